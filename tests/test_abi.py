@@ -1,0 +1,62 @@
+"""CPU checks of the drop-in boundary: the library loads and exports every symbol include/uml_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "uml_b200.h").read_text()
+    return sorted(set(re.findall(r"^UML_API [^;(]*?\b(uml_[a-z0-9_]+)\(", text, flags=re.M)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from unionml_b200 import _build
+
+    return _build.build()
+
+
+def test_header_declares_expected_surface():
+    syms = _declared_symbols()
+    for name in ("uml_engine_create", "uml_linear_load", "uml_stage_rows", "uml_linear_predict",
+                 "uml_linear_predict_peers", "uml_linear_predict_host", "uml_last_error"):
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    handle = ctypes.CDLL(str(built_lib))
+    missing = [s for s in _declared_symbols() if not hasattr(handle, s)]
+    assert not missing, missing
+    handle.uml_abi_version.restype = ctypes.c_int
+    assert handle.uml_abi_version() == 1
+
+
+def test_python_binding_covers_the_header(built_lib):
+    from unionml_b200 import _native
+
+    assert sorted(_native.SIGNATURES) == _declared_symbols()
+    _native.lib()  # argtypes/restype resolve for every symbol
+
+
+def test_no_device_fails_loudly(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from unionml_b200.engine import Engine
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(0)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under unionml_b200/ may reference it."""
+    for path in (ROOT / "unionml_b200").rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".h"}:
+            text = path.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+            assert "oracle/" not in text and "oracle." not in text.replace("oracle.unionml_path", ""), path

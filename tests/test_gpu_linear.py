@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bar: labels are index work -> bit-exact.  In EXACT mode the engine's labels must equal the float64 oracle
+(= scikit-learn's float64 path) on every row.  In FAST mode (plain fp32) differences are only allowed on rows whose
+float64 top-2 margin is below the fp32 error bound, and the test states that bound.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import linear as olin
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU boxes, skipped there (the -m gpu run happens on the B200)
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from unionml_b200.engine import Engine
+
+    return Engine(0)
+
+
+def digits_rows(seed, rows, dtype=np.float32):
+    return np.random.default_rng(seed).integers(0, 17, size=(rows, 64), dtype=np.uint8).astype(dtype)
+
+
+def oracle_idx(X, coef, intercept):
+    return olin.predict_indices(olin.decision_function(np.asarray(X, dtype=np.float64), coef, intercept)).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors
+# ---------------------------------------------------------------------------------------------------------------
+def test_known_answer_through_predictor(digits_model, known_answer):
+    """[8.0, 8.0, 0.0]: /root/reference/tests/unit/test_aws_lambda_handler.py:127,159 - now on the GPU."""
+    from sklearn.linear_model import LogisticRegression
+
+    from unionml_b200.predictors import linear_argmax
+
+    est = LogisticRegression()
+    est.coef_, est.intercept_, est.classes_ = digits_model["coef"], digits_model["intercept"], digits_model["classes"]
+    est.n_features_in_ = 64
+    for key, want in (("sample3_random_state99", [8.0, 8.0, 0.0]), ("sample5_random_state42", [6.0, 9.0, 3.0, 7.0, 2.0])):
+        frame = pd.DataFrame(known_answer[key]["records"])[known_answer["feature_names"]]
+        got = linear_argmax(est, frame)
+        assert got == want
+        assert all(isinstance(x, float) for x in got)
+
+
+def test_committed_fixture(engine, digits_model, synthetic_digits):
+    m = engine.load_linear(digits_model["coef"], digits_model["intercept"], digits_model["classes"])
+    X = synthetic_digits["X"]
+    for arr in (X.astype(np.float32), X.astype(np.float64), X, np.asfortranarray(X.astype(np.float64))):
+        idx, stats = engine.predict_host(m, arr, exact=True)
+        np.testing.assert_array_equal(digits_model["classes"][idx], synthetic_digits["labels_f64"])
+        b = engine.stage(arr)
+        idx2, st2 = engine.predict(m, b, exact=True)
+        np.testing.assert_array_equal(idx2, idx)
+        assert st2["path"] == 1 and st2["kernel_launches"] == 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# seeded parity at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows", [1, 31, 127, 128, 129, 1000, 4097, 300_001])
+def test_exact_parity_ragged_sizes(engine, digits_model, rows):
+    m = engine.load_linear(digits_model["coef"], digits_model["intercept"])
+    X = digits_rows(rows, rows)
+    want = oracle_idx(X, digits_model["coef"], digits_model["intercept"])
+    got, stats = engine.predict(m, engine.stage(X), exact=True)
+    np.testing.assert_array_equal(got, want)
+    assert stats["n_rows"] == rows and stats["n_nonfinite"] == 0
+    got_h, _ = engine.predict_host(m, X, exact=True, chunk_rows=1024)
+    np.testing.assert_array_equal(got_h, want)
+
+
+def test_empty_batch(engine, digits_model):
+    m = engine.load_linear(digits_model["coef"], digits_model["intercept"])
+    X = np.zeros((0, 64), dtype=np.float32)
+    got, _ = engine.predict_host(m, X)
+    assert got.shape == (0,)
+    got, _ = engine.predict(m, engine.stage(X))
+    assert got.shape == (0,)
+
+
+def test_exact_vs_fast_two_million(engine, digits_model):
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    m = engine.load_linear(coef, intercept)
+    X = np.concatenate([digits_rows(k, 500_000) for k in range(4)])
+    scores = olin.decision_function(X.astype(np.float64), coef, intercept)
+    want = olin.predict_indices(scores).astype(np.int32)
+    b = engine.stage(X)
+    exact, st = engine.predict(m, b, exact=True)
+    np.testing.assert_array_equal(exact, want)
+    # the guard flags few rows (< 0.1 %) and re-scores them; none is a genuine float64 tie on this data
+    assert 0 < st["n_flagged"] < 2000, st
+    assert st["n_ambiguous"] == 0
+    fast, stf = engine.predict(m, b, exact=False)
+    assert stf["kernel_launches"] == 1
+    diff = np.flatnonzero(fast != want)
+    # fp32 error bound of a 64-term FMA chain: (F+4) 2^-24 * (|b| + sum |x w|)  <=  68 * 6e-8 * A
+    A = np.abs(intercept).max() + np.abs(X.astype(np.float64)) @ np.abs(coef).max(axis=0)
+    margin = olin.top2_margin(scores)
+    assert np.all(margin[diff] <= 2 * 68 * 2.0**-24 * A[diff])
+    assert len(diff) < 50
+
+
+def test_layouts_and_dtypes(engine, digits_model):
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    m = engine.load_linear(coef, intercept)
+    base = digits_rows(7, 50_000, np.float64)
+    want = oracle_idx(base, coef, intercept)
+    frame = pd.DataFrame(base, columns=[f"pixel_{i}" for i in range(64)])  # pandas block: feature-major
+    wide = np.zeros((50_000, 80), dtype=np.float32)
+    wide[:, :64] = base
+    variants = {
+        "f64_c": base,
+        "f64_f": np.asfortranarray(base),
+        "f32_c": base.astype(np.float32),
+        "f32_f": np.asfortranarray(base.astype(np.float32)),
+        "i64": base.astype(np.int64),
+        "i32_f": np.asfortranarray(base.astype(np.int32)),
+        "u8": base.astype(np.uint8),
+        "frame": frame,
+        "row_strided": wide[:, :64],
+        "noncontig": base[::2],
+    }
+    for name, arr in variants.items():
+        w = want[::2] if name == "noncontig" else want
+        got, _ = engine.predict_host(m, arr, exact=True)
+        np.testing.assert_array_equal(got, w, err_msg=name)
+        got2, _ = engine.predict(m, engine.stage(arr), exact=True)
+        np.testing.assert_array_equal(got2, w, err_msg=name)
+
+
+def test_lossy_float64_features_use_the_f64_copy(engine):
+    """Features that do not survive the fp32 down-cast: exact mode re-scores flagged rows from the float64 copy."""
+    rng = np.random.default_rng(5)
+    coef = rng.standard_normal((5, 12))
+    intercept = rng.standard_normal(5)
+    X = rng.standard_normal((100_000, 12))
+    # plant near-ties that only float64 features resolve
+    X[:1000] = X[0]
+    X[:1000, 3] += np.linspace(-1e-9, 1e-9, 1000)
+    want = oracle_idx(X, coef, intercept)
+    m = engine.load_linear(coef, intercept)
+    b = engine.stage(X, keep_f64=True)
+    assert not b.lossless
+    got, st = engine.predict(m, b, exact=True)
+    np.testing.assert_array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tie / edge semantics
+# ---------------------------------------------------------------------------------------------------------------
+def test_ties_first_maximum_wins(engine):
+    coef = np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 1.0]])
+    intercept = np.zeros(4)
+    X = np.array([[2.0, 1.0], [1.0, 2.0], [1.0, 1.0], [0.0, 0.0]], dtype=np.float32)
+    m = engine.load_linear(coef, intercept)
+    for exact in (True, False):
+        got, st = engine.predict(m, engine.stage(X), exact=exact)
+        np.testing.assert_array_equal(got, [0, 2, 0, 0])
+    np.testing.assert_array_equal(olin.exact_predict_indices(X, coef, intercept), [0, 2, 0, 0])
+
+
+def test_binary_model(engine, binary_mock):
+    m = engine.load_linear(binary_mock["coef"], binary_mock["intercept"], binary_mock["classes"])
+    got, _ = engine.predict_host(m, binary_mock["X"], exact=True)
+    np.testing.assert_array_equal(binary_mock["classes"][got], binary_mock["labels"])
+    # score exactly zero -> class 0 (strict '>' of _base.py:416)
+    m0 = engine.load_linear(np.array([[1.0]]), np.array([0.0]))
+    got, _ = engine.predict_host(m0, np.array([[0.0], [1e-30], [-1.0]]), exact=True)
+    np.testing.assert_array_equal(got, [0, 1, 0])
+
+
+@pytest.mark.parametrize("n_classes", [2, 3, 7, 10, 16, 17, 40])
+@pytest.mark.parametrize("n_features", [1, 3, 33, 64, 100])
+def test_shapes(engine, n_classes, n_features):
+    rng = np.random.default_rng(n_classes * 1000 + n_features)
+    coef = rng.standard_normal((n_classes, n_features))
+    intercept = rng.standard_normal(n_classes)
+    X = rng.integers(-8, 9, size=(20_011, n_features)).astype(np.float32)
+    want = oracle_idx(X, coef, intercept)
+    m = engine.load_linear(coef, intercept)
+    got, st = engine.predict(m, engine.stage(X), exact=True)
+    np.testing.assert_array_equal(got, want)
+    assert st["path"] == (1 if n_classes <= 16 else 2)
+
+
+def test_mnist_shape_784(engine):
+    rng = np.random.default_rng(1)
+    coef = (rng.standard_normal((10, 784)) * 0.05).astype(np.float32)
+    intercept = np.random.default_rng(2).standard_normal(10).astype(np.float32)
+    X = (rng.integers(0, 256, size=(100_000, 784)).astype(np.float32)) / np.float32(255.0)
+    want = oracle_idx(X, coef.astype(np.float64), intercept.astype(np.float64))
+    m = engine.load_linear(coef, intercept)
+    got, st = engine.predict(m, engine.stage(X), exact=True)
+    np.testing.assert_array_equal(got, want)
+    assert st["path"] == 1
+
+
+def test_affine_fold_matches_scaler_pipeline(engine, digits_model):
+    """Pipeline(StandardScaler, LogisticRegression) of docs/tutorials/mnist.md:116-124, scaler folded into W, b."""
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    X = digits_rows(11, 100_000, np.float64)
+    mu, sd = X.mean(axis=0), X.std(axis=0) + 0.5
+    want = oracle_idx((X - mu) / sd, coef, intercept)
+    m = engine.load_linear(coef, intercept)
+    m.set_affine(shift=mu, scale=1.0 / sd)
+    got, _ = engine.predict_host(m, X, exact=True)
+    assert (got != want).sum() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# errors at the boundary
+# ---------------------------------------------------------------------------------------------------------------
+def test_nonfinite_raises_value_error(engine, digits_model):
+    m = engine.load_linear(digits_model["coef"], digits_model["intercept"])
+    for bad_value in (np.nan, np.inf, -np.inf):
+        X = digits_rows(3, 5000)
+        X[4321, 17] = bad_value
+        with pytest.raises(ValueError):
+            engine.predict_host(m, X, exact=True)
+        with pytest.raises(ValueError):
+            engine.predict_host(m, X, exact=False)
+        with pytest.raises(ValueError):
+            engine.stage(X)
+        # device-resident rows that never went through staging: exact mode still catches it
+        b = engine.stage(X, check_finite=False)
+        with pytest.raises(ValueError):
+            engine.predict(m, b, exact=True)
+
+
+def test_wrong_feature_count(engine, digits_model):
+    m = engine.load_linear(digits_model["coef"], digits_model["intercept"])
+    with pytest.raises(ValueError, match="63 features"):
+        engine.predict_host(m, np.zeros((4, 63), dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full BASELINE size (10M x 64): size-independent properties + streamed oracle comparison
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_ten_million(engine, digits_model):
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    m = engine.load_linear(coef, intercept)
+    N = 10_000_000
+    X = engine.pinned_empty((N, 64), np.float32)
+    for k in range(10):
+        X[k * 1_000_000 : (k + 1) * 1_000_000] = digits_rows(k, 1_000_000)
+    b = engine.stage(X)
+    labels, st = engine.predict(m, b, exact=True)
+    assert st["n_rows"] == N and st["n_ambiguous"] == 0 and 0 < st["n_flagged"] < N // 1000
+    # (1) every row against the float64 oracle, streamed in 1M-row chunks
+    for k in range(10):
+        sl = slice(k * 1_000_000, (k + 1) * 1_000_000)
+        np.testing.assert_array_equal(labels[sl], oracle_idx(X[sl], coef, intercept))
+    # (2) chunking invariance: host-streamed path == resident path
+    streamed, _ = engine.predict_host(m, X, exact=True)
+    np.testing.assert_array_equal(streamed, labels)
+    # (3) permutation equivariance on a shuffled million
+    perm = np.random.default_rng(0).permutation(1_000_000)
+    sub, _ = engine.predict_host(m, X[:1_000_000][perm], exact=True)
+    np.testing.assert_array_equal(sub, labels[:1_000_000][perm])
+    # (4) label histogram is a checksum that must agree between modes except on flagged rows
+    fast, _ = engine.predict(m, b, exact=False)
+    assert (fast != labels).sum() <= st["n_flagged"]

@@ -1,0 +1,826 @@
+// C ABI of the uml_b200 engine (see include/uml_b200.h): device binding, model/batch residency, predict calls.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "uml_common.cuh"
+
+namespace uml {
+cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
+                               cudaStream_t stream);
+}
+
+using uml::FlagList;
+using uml::LinearDeviceModel;
+using uml::LinearLaunch;
+using uml::StageResult;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static thread_local std::string g_create_error;
+
+struct HostMirror {  // pinned; device counters are copied here
+  int flag_count;
+  int pad;
+  unsigned long long counters[4];
+  StageResult stage;
+};
+
+struct uml_engine {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  cudaEvent_t chunk_ev[8] = {};
+  uml_device_info info{};
+  PFN_encodeTiled encode = nullptr;
+  std::string last_error;
+  // device scratch
+  int* d_flag_count = nullptr;
+  unsigned long long* d_counters = nullptr;
+  StageResult* d_stage = nullptr;
+  int32_t* d_flag_rows = nullptr;
+  int64_t flag_cap = 0;
+  int32_t* d_labels = nullptr;
+  int64_t labels_cap = 0;
+  void* d_chunk[3] = {nullptr, nullptr, nullptr};  // raw source chunks (staging / predict_host)
+  int64_t chunk_cap = 0;
+  float* d_xchunk[3] = {nullptr, nullptr, nullptr};  // converted fp32 chunks (predict_host)
+  int64_t xchunk_cap = 0;
+  HostMirror* h = nullptr;
+};
+
+struct uml_model {
+  uml_engine* e = nullptr;
+  LinearDeviceModel dm{};
+  int n_features_in = 0;
+  int n_classes_in = 0;  // as passed by the caller (1 for sklearn's binary layout)
+  std::vector<double> coef64, intercept64;  // caller's values (expanded), before any affine fold
+  float* d_wt = nullptr;
+  float* d_bias = nullptr;
+  double* d_w64 = nullptr;
+  double* d_b64 = nullptr;
+};
+
+struct uml_batch {
+  uml_engine* e = nullptr;
+  float* x = nullptr;
+  double* x64 = nullptr;
+  int64_t n_rows = 0, ld = 0, ld64 = 0;
+  int n_features = 0;
+  bool owns = false;
+  bool lossless = true;
+  bool has_map = false;
+  CUtensorMap map{};
+};
+
+struct uml_mlp {
+  uml_engine* e = nullptr;
+};
+
+#define UML_FAIL(E, CODE, ...)                              \
+  do {                                                      \
+    char _buf[512];                                         \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);              \
+    if (E) (E)->last_error = _buf; else g_create_error = _buf; \
+    return (CODE);                                          \
+  } while (0)
+
+#define UML_CUDA(E, CALL)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _err = (CALL);                                                                         \
+    if (_err != cudaSuccess) {                                                                         \
+      UML_FAIL(E, _err == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA, "%s failed: %s", #CALL, \
+               cudaGetErrorString(_err));                                                              \
+    }                                                                                                  \
+  } while (0)
+
+static int dtype_size(int dt) {
+  switch (dt) {
+    case UML_F32: return 4;
+    case UML_F64: return 8;
+    case UML_I64: return 8;
+    case UML_I32: return 4;
+    case UML_U8: return 1;
+    default: return 0;
+  }
+}
+
+extern "C" {
+
+int uml_abi_version(void) { return UML_B200_ABI_VERSION; }
+
+const char* uml_last_error(const uml_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+int uml_engine_create(uml_engine** out, int device_id) {
+  if (!out) UML_FAIL((uml_engine*)nullptr, UML_ERR_INVALID, "uml_engine_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0)
+    UML_FAIL((uml_engine*)nullptr, UML_ERR_NO_DEVICE, "no CUDA device visible (%s); uml_b200 has no CPU fallback",
+             err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+  if (device_id < 0 || device_id >= n)
+    UML_FAIL((uml_engine*)nullptr, UML_ERR_INVALID, "device_id %d out of range [0,%d)", device_id, n);
+  uml_engine* e = new uml_engine();
+  e->device = device_id;
+  auto fail = [&](const char* what, cudaError_t ce) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(ce));
+    g_create_error = buf;
+    delete e;
+    return (int)UML_ERR_CUDA;
+  };
+  if ((err = cudaSetDevice(device_id)) != cudaSuccess) return fail("cudaSetDevice", err);
+  cudaDeviceProp prop;
+  if ((err = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return fail("cudaGetDeviceProperties", err);
+  e->info.device_id = device_id;
+  e->info.sm_count = prop.multiProcessorCount;
+  e->info.cc_major = prop.major;
+  e->info.cc_minor = prop.minor;
+  e->info.total_mem_bytes = (int64_t)prop.totalGlobalMem;
+  e->info.l2_bytes = prop.l2CacheSize;
+  cudaDeviceGetAttribute(&e->info.sm_clock_khz, cudaDevAttrClockRate, device_id);
+  cudaDeviceGetAttribute(&e->info.mem_clock_khz, cudaDevAttrMemoryClockRate, device_id);
+  strncpy(e->info.name, prop.name, sizeof(e->info.name) - 1);
+  if (prop.major != 10) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "device %d (%s) is compute capability %d.%d; this library is built for sm_100a only",
+             device_id, prop.name, prop.major, prop.minor);
+    g_create_error = buf;
+    delete e;
+    return UML_ERR_NO_DEVICE;
+  }
+  if ((err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail("cudaStreamCreate", err);
+  if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail("cudaStreamCreate", err);
+  e->stream = e->own_stream;
+  for (auto& ev : e->ev)
+    if ((err = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", err);
+  for (auto& ev : e->chunk_ev)
+    if ((err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", err);
+  if ((err = cudaMalloc(&e->d_flag_count, sizeof(int))) != cudaSuccess) return fail("cudaMalloc", err);
+  if ((err = cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", err);
+  if ((err = cudaMalloc(&e->d_stage, sizeof(StageResult))) != cudaSuccess) return fail("cudaMalloc", err);
+  if ((err = cudaHostAlloc((void**)&e->h, sizeof(HostMirror), cudaHostAllocDefault)) != cudaSuccess)
+    return fail("cudaHostAlloc", err);
+  memset(e->h, 0, sizeof(HostMirror));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return fail("cuTensorMapEncodeTiled lookup", err);
+  e->encode = (PFN_encodeTiled)fn;
+  *out = e;
+  return UML_OK;
+}
+
+void uml_engine_destroy(uml_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  cudaFree(e->d_flag_count);
+  cudaFree(e->d_counters);
+  cudaFree(e->d_stage);
+  cudaFree(e->d_flag_rows);
+  cudaFree(e->d_labels);
+  for (auto p : e->d_chunk) cudaFree(p);
+  for (auto p : e->d_xchunk) cudaFree(p);
+  if (e->h) cudaFreeHost(e->h);
+  for (auto ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto ev : e->chunk_ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  delete e;
+}
+
+int uml_engine_info(const uml_engine* e, uml_device_info* out) {
+  if (!e || !out) return UML_ERR_INVALID;
+  *out = e->info;
+  return UML_OK;
+}
+
+int uml_engine_set_stream(uml_engine* e, void* cuda_stream) {
+  if (!e) return UML_ERR_INVALID;
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return UML_OK;
+}
+
+int uml_engine_synchronize(uml_engine* e) {
+  if (!e) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  UML_CUDA(e, cudaStreamSynchronize(e->stream));
+  UML_CUDA(e, cudaStreamSynchronize(e->copy_stream));
+  return UML_OK;
+}
+
+int uml_host_alloc(uml_engine* e, void** out, int64_t bytes) {
+  if (!e || !out || bytes < 0) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  UML_CUDA(e, cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+  return UML_OK;
+}
+
+int uml_host_free(uml_engine* e, void* p) {
+  if (!e) return UML_ERR_INVALID;
+  if (p) UML_CUDA(e, cudaFreeHost(p));
+  return UML_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------------
+static int upload_model(uml_engine* e, uml_model* m, const std::vector<double>& w, const std::vector<double>& b) {
+  const int C = m->dm.n_classes, F = m->dm.n_features;
+  const int cp = (C + 1 + 3) / 4 * 4;
+  const int f_pad = (F + uml::kChunkF - 1) / uml::kChunkF * uml::kChunkF;
+  std::vector<float> wt((size_t)f_pad * cp, 0.f), bias(cp, 0.f);
+  float bmax = 0.f;
+  for (int c = 0; c < C; ++c) {
+    bias[c] = (float)b[c];
+    bmax = fmaxf(bmax, fabsf(bias[c]));
+  }
+  bias[C] = bmax;
+  for (int f = 0; f < F; ++f) {
+    float wmax = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = (float)w[(size_t)c * F + f];
+      wt[(size_t)f * cp + c] = v;
+      wmax = fmaxf(wmax, fabsf(v));
+    }
+    wt[(size_t)f * cp + C] = wmax;
+  }
+  auto ensure = [&](void** p, size_t bytes) -> cudaError_t {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc(p, bytes);
+  };
+  UML_CUDA(e, ensure((void**)&m->d_wt, wt.size() * 4));
+  UML_CUDA(e, ensure((void**)&m->d_bias, bias.size() * 4));
+  UML_CUDA(e, ensure((void**)&m->d_w64, w.size() * 8));
+  UML_CUDA(e, ensure((void**)&m->d_b64, b.size() * 8));
+  UML_CUDA(e, cudaMemcpy(m->d_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+  UML_CUDA(e, cudaMemcpy(m->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  UML_CUDA(e, cudaMemcpy(m->d_w64, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+  UML_CUDA(e, cudaMemcpy(m->d_b64, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+  m->dm.wt = m->d_wt;
+  m->dm.bias = m->d_bias;
+  m->dm.w64 = m->d_w64;
+  m->dm.b64 = m->d_b64;
+  m->dm.cp = cp;
+  m->dm.f_pad = f_pad;
+  return UML_OK;
+}
+
+int uml_linear_load(uml_engine* e, uml_model** out, const void* coef, const void* intercept, int n_classes,
+                    int n_features, int dtype) {
+  if (!e || !out || !coef || !intercept) return UML_ERR_INVALID;
+  *out = nullptr;
+  if (n_classes < 1 || n_features < 1) UML_FAIL(e, UML_ERR_INVALID, "n_classes=%d n_features=%d", n_classes, n_features);
+  if (dtype != UML_F32 && dtype != UML_F64) UML_FAIL(e, UML_ERR_INVALID, "coef dtype must be F32 or F64");
+  UML_CUDA(e, cudaSetDevice(e->device));
+  auto get = [&](const void* p, size_t i) -> double {
+    return dtype == UML_F64 ? ((const double*)p)[i] : (double)((const float*)p)[i];
+  };
+  uml_model* m = new uml_model();
+  m->e = e;
+  m->n_features_in = n_features;
+  m->n_classes_in = n_classes;
+  const int C = n_classes == 1 ? 2 : n_classes;  // binary: scores > 0  <=>  argmax([0, s]) with first-max ties
+  const int F = n_features;
+  m->coef64.assign((size_t)C * F, 0.0);
+  m->intercept64.assign(C, 0.0);
+  const int c0 = n_classes == 1 ? 1 : 0;
+  for (int c = 0; c < n_classes; ++c) {
+    for (int f = 0; f < F; ++f) m->coef64[(size_t)(c + c0) * F + f] = get(coef, (size_t)c * F + f);
+    m->intercept64[c + c0] = get(intercept, c);
+  }
+  m->dm.n_classes = C;
+  m->dm.n_features = F;
+  int rc = upload_model(e, m, m->coef64, m->intercept64);
+  if (rc != UML_OK) {
+    uml_model_free(m);
+    return rc;
+  }
+  *out = m;
+  return UML_OK;
+}
+
+int uml_linear_set_affine(uml_engine* e, uml_model* m, const double* shift, const double* scale) {
+  if (!e || !m) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  const int C = m->dm.n_classes, F = m->dm.n_features;
+  std::vector<double> w = m->coef64, b = m->intercept64;
+  // s_c = sum_f ((x_f - shift_f) * scale_f) w_cf + b_c = sum_f x_f (scale_f w_cf) + (b_c - sum_f shift_f scale_f w_cf)
+  for (int c = 0; c < C; ++c) {
+    double acc = b[c];
+    for (int f = 0; f < F; ++f) {
+      const double sc = scale ? scale[f] : 1.0;
+      const double sh = shift ? shift[f] : 0.0;
+      const double wf = w[(size_t)c * F + f] * sc;
+      w[(size_t)c * F + f] = wf;
+      acc -= sh * wf;
+    }
+    b[c] = acc;
+  }
+  return upload_model(e, m, w, b);
+}
+
+void uml_model_free(uml_model* m) {
+  if (!m) return;
+  if (m->e) cudaSetDevice(m->e->device);
+  cudaFree(m->d_wt);
+  cudaFree(m->d_bias);
+  cudaFree(m->d_w64);
+  cudaFree(m->d_b64);
+  delete m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch
+// ---------------------------------------------------------------------------------------------------------------
+static int encode_map(uml_engine* e, CUtensorMap* map, const float* x, int64_t n_rows, int F, int64_t ld) {
+  if (((uintptr_t)x & 15) != 0 || (ld % 4) != 0) UML_FAIL(e, UML_ERR_UNSUPPORTED, "rows must be 16-byte aligned with ld %% 4 == 0");
+  if (n_rows >= (1ll << 31) - uml::kTileRows) UML_FAIL(e, UML_ERR_UNSUPPORTED, "more than 2^31 rows in one batch");
+  cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)n_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)uml::kChunkF, (cuuint32_t)uml::kTileRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) UML_FAIL(e, UML_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld x %d ld %lld", (int)r,
+                                  (long long)n_rows, F, (long long)ld);
+  return UML_OK;
+}
+
+int uml_batch_from_device(uml_engine* e, uml_batch** out, const void* dev_ptr, int64_t n_rows, int n_features,
+                          int64_t ld) {
+  if (!e || !out || (!dev_ptr && n_rows > 0) || n_rows < 0 || n_features < 1 || ld < n_features) return UML_ERR_INVALID;
+  *out = nullptr;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  uml_batch* b = new uml_batch();
+  b->e = e;
+  b->x = (float*)dev_ptr;
+  b->n_rows = n_rows;
+  b->n_features = n_features;
+  b->ld = ld;
+  b->owns = false;
+  if (n_rows > 0) {
+    int rc = encode_map(e, &b->map, b->x, n_rows, n_features, ld);
+    if (rc == UML_OK) b->has_map = true;
+    else if (rc != UML_ERR_UNSUPPORTED) {
+      delete b;
+      return rc;
+    }
+  }
+  *out = b;
+  return UML_OK;
+}
+
+static int ensure_chunks(uml_engine* e, int64_t bytes) {
+  if (e->chunk_cap >= bytes) return UML_OK;
+  for (auto& p : e->d_chunk) {
+    cudaFree(p);
+    p = nullptr;
+  }
+  e->chunk_cap = 0;
+  for (auto& p : e->d_chunk) UML_CUDA(e, cudaMalloc(&p, (size_t)bytes));
+  e->chunk_cap = bytes;
+  return UML_OK;
+}
+
+struct SrcLayout {
+  bool feature_major;
+  int64_t pitch_elems;
+  int elem;
+};
+
+static int classify_layout(uml_engine* e, int64_t n_rows, int F, int64_t rs, int64_t cs, int dtype, SrcLayout* L) {
+  const int elem = dtype_size(dtype);
+  if (!elem) UML_FAIL(e, UML_ERR_INVALID, "unknown dtype %d", dtype);
+  L->elem = elem;
+  if (cs == elem || F == 1) {
+    if (rs % elem != 0 || rs < (int64_t)F * elem) {
+      if (n_rows > 1) UML_FAIL(e, UML_ERR_UNSUPPORTED, "row stride %lld not a multiple of the element size / overlaps", (long long)rs);
+      rs = (int64_t)F * elem;
+    }
+    L->feature_major = false;
+    L->pitch_elems = rs / elem;
+    return UML_OK;
+  }
+  if (rs == elem || n_rows == 1) {
+    if (cs % elem != 0 || cs < n_rows * elem) UML_FAIL(e, UML_ERR_UNSUPPORTED, "column stride %lld unsupported", (long long)cs);
+    L->feature_major = true;
+    L->pitch_elems = cs / elem;
+    return UML_OK;
+  }
+  UML_FAIL(e, UML_ERR_UNSUPPORTED, "features must be contiguous along rows or along columns (strides %lld, %lld bytes)",
+           (long long)rs, (long long)cs);
+}
+
+// copy rows [r0, r0+rows) of the host source into device chunk buffer `dst` (compact: pitch = F or rows elements)
+static cudaError_t copy_chunk_h2d(void* dst, const void* host, const SrcLayout& L, int64_t r0, int64_t rows, int F,
+                                  cudaStream_t s) {
+  const char* src = (const char*)host;
+  if (!L.feature_major) {
+    const size_t width = (size_t)F * L.elem;
+    const size_t spitch = (size_t)L.pitch_elems * L.elem;
+    if (spitch == width) return cudaMemcpyAsync(dst, src + (size_t)r0 * spitch, width * rows, cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, width, src + (size_t)r0 * spitch, spitch, width, (size_t)rows, cudaMemcpyHostToDevice, s);
+  }
+  const size_t width = (size_t)rows * L.elem;
+  const size_t spitch = (size_t)L.pitch_elems * L.elem;
+  return cudaMemcpy2DAsync(dst, width, src + (size_t)r0 * L.elem, spitch, width, (size_t)F, cudaMemcpyHostToDevice, s);
+}
+
+int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t n_rows, int n_features,
+                   int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, uint32_t flags) {
+  if (!e || !out || (!host_ptr && n_rows > 0) || n_rows < 0 || n_features < 1) return UML_ERR_INVALID;
+  *out = nullptr;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  (void)cudaGetLastError();
+  SrcLayout L{};
+  int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
+  if (rc != UML_OK) return rc;
+  const int F = n_features;
+  const int64_t ld = (F + 3) / 4 * 4;
+  const bool check = !(flags & UML_STAGE_SKIP_FINITE_CHECK);
+  const bool want64 = (flags & UML_STAGE_KEEP_F64) && (src_dtype == UML_F64 || src_dtype == UML_I64);
+
+  uml_batch* b = new uml_batch();
+  b->e = e;
+  b->n_rows = n_rows;
+  b->n_features = F;
+  b->ld = ld;
+  b->owns = true;
+  auto bail = [&](int code) {
+    uml_batch_free(b);
+    return code;
+  };
+  if (n_rows == 0) {
+    *out = b;
+    return UML_OK;
+  }
+  cudaError_t ce;
+  if ((ce = cudaMalloc((void**)&b->x, (size_t)n_rows * ld * 4)) != cudaSuccess) {
+    e->last_error = std::string("cudaMalloc(batch): ") + cudaGetErrorString(ce);
+    return bail(ce == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA);
+  }
+  if (want64) {
+    b->ld64 = F;
+    if ((ce = cudaMalloc((void**)&b->x64, (size_t)n_rows * F * 8)) != cudaSuccess) {
+      e->last_error = std::string("cudaMalloc(batch f64): ") + cudaGetErrorString(ce);
+      return bail(ce == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA);
+    }
+  }
+  cudaStream_t cs = e->stream;
+#define STAGE_CUDA(CALL)                                                            \
+  do {                                                                              \
+    cudaError_t _e2 = (CALL);                                                       \
+    if (_e2 != cudaSuccess) {                                                       \
+      e->last_error = std::string(#CALL) + ": " + cudaGetErrorString(_e2);          \
+      cudaStreamSynchronize(cs);                                                    \
+      cudaStreamSynchronize(e->copy_stream);                                        \
+      return bail(UML_ERR_CUDA);                                                    \
+    }                                                                               \
+  } while (0)
+  STAGE_CUDA(cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), cs));
+
+  const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld;
+  if (direct) {
+    // already the resident layout: one straight H2D, then the finiteness scan
+    STAGE_CUDA(cudaMemcpyAsync(b->x, host_ptr, (size_t)n_rows * ld * 4, cudaMemcpyHostToDevice, cs));
+    if (check) STAGE_CUDA(uml::launch_finite_scan(b->x, ld, n_rows, F, e->d_stage, cs));
+  } else {
+    // chunked: H2D of raw source bytes on the copy stream, transpose/convert kernel on the compute stream
+    const int64_t row_bytes = (int64_t)F * L.elem;
+    int64_t chunk_rows = std::max<int64_t>(1024, (64ll << 20) / row_bytes);
+    chunk_rows = std::min<int64_t>((chunk_rows + 31) / 32 * 32, std::max<int64_t>(n_rows, 1));
+    int rc2 = ensure_chunks(e, chunk_rows * row_bytes);
+    if (rc2 != UML_OK) return bail(rc2);
+    int slot = 0;
+    bool used[3] = {false, false, false};
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
+      const int64_t rows = std::min(chunk_rows, n_rows - r0);
+      if (used[slot]) STAGE_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));  // convert done
+      STAGE_CUDA(copy_chunk_h2d(e->d_chunk[slot], host_ptr, L, r0, rows, F, e->copy_stream));
+      STAGE_CUDA(cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
+      STAGE_CUDA(cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
+      STAGE_CUDA(uml::launch_stage_convert(e->d_chunk[slot], src_dtype, L.feature_major, L.feature_major ? rows : F,
+                                           rows, F, b->x + r0 * ld, ld, b->x64 ? b->x64 + r0 * b->ld64 : nullptr,
+                                           b->ld64, e->d_stage, check, cs));
+      STAGE_CUDA(cudaEventRecord(e->chunk_ev[3 + slot], cs));
+      used[slot] = true;
+    }
+  }
+  STAGE_CUDA(cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
+  STAGE_CUDA(cudaStreamSynchronize(cs));
+#undef STAGE_CUDA
+  if (check && e->h->stage.nonfinite) {
+    e->last_error = "Input X contains NaN or infinity.";
+    return bail(UML_ERR_NONFINITE);
+  }
+  b->lossless = direct ? true : e->h->stage.lossy == 0;
+  if (b->x64 && b->lossless) {
+    cudaFree(b->x64);
+    b->x64 = nullptr;
+  }
+  rc = encode_map(e, &b->map, b->x, n_rows, F, ld);
+  if (rc == UML_OK) b->has_map = true;
+  else if (rc != UML_ERR_UNSUPPORTED) return bail(rc);
+  *out = b;
+  return UML_OK;
+}
+
+int uml_batch_info(const uml_batch* b, int64_t* n_rows, int* n_features, int64_t* ld, const void** dev_ptr,
+                   int* lossless) {
+  if (!b) return UML_ERR_INVALID;
+  if (n_rows) *n_rows = b->n_rows;
+  if (n_features) *n_features = b->n_features;
+  if (ld) *ld = b->ld;
+  if (dev_ptr) *dev_ptr = b->x;
+  if (lossless) *lossless = b->lossless ? 1 : 0;
+  return UML_OK;
+}
+
+void uml_batch_free(uml_batch* b) {
+  if (!b) return;
+  if (b->e) cudaSetDevice(b->e->device);
+  if (b->owns) cudaFree(b->x);
+  cudaFree(b->x64);
+  delete b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// predict
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_flags(uml_engine* e, int64_t rows) {
+  if (e->flag_cap >= rows) return UML_OK;
+  cudaFree(e->d_flag_rows);
+  e->d_flag_rows = nullptr;
+  e->flag_cap = 0;
+  UML_CUDA(e, cudaMalloc((void**)&e->d_flag_rows, (size_t)rows * 4));
+  e->flag_cap = rows;
+  return UML_OK;
+}
+
+static int ensure_labels(uml_engine* e, int64_t rows) {
+  if (e->labels_cap >= rows) return UML_OK;
+  cudaFree(e->d_labels);
+  e->d_labels = nullptr;
+  e->labels_cap = 0;
+  UML_CUDA(e, cudaMalloc((void**)&e->d_labels, (size_t)rows * 4));
+  e->labels_cap = rows;
+  return UML_OK;
+}
+
+// enqueue the scoring of one resident block of rows on e->stream; no host synchronisation.
+// ev_k (optional) brackets the scoring kernel, ev_r the fp64 re-score.
+static int enqueue_predict(uml_engine* e, const uml_model* m, const LinearLaunch& l, const CUtensorMap* map, int mode,
+                           bool timed, int* launches, int* path) {
+  FlagList fl{e->d_flag_count, e->d_flag_rows, (int)std::min<int64_t>(e->flag_cap, INT32_MAX), e->d_counters};
+  const bool exact = mode == UML_PREDICT_EXACT;
+  std::string why;
+  const bool tma = map != nullptr && uml::linear_tma_supported(m->dm, &why);
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[1], e->stream));
+  if (tma) {
+    if (exact) UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+    std::string err;
+    cudaError_t ce = uml::launch_linear_tma(*map, m->dm, l, exact, fl, e->info.sm_count, e->stream, &err);
+    if (ce != cudaSuccess) UML_FAIL(e, UML_ERR_CUDA, "linear_argmax_tma launch: %s %s", cudaGetErrorString(ce), err.c_str());
+    *launches += 1;
+    *path = 1;
+    if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
+    if (exact) {
+      UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, false, e->info.sm_count, e->stream));
+      *launches += 1;
+    }
+    if (timed) UML_CUDA(e, cudaEventRecord(e->ev[3], e->stream));
+  } else {
+    UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, true, e->info.sm_count, e->stream));
+    *launches += 1;
+    *path = 2;
+    if (timed) {
+      UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
+      UML_CUDA(e, cudaEventRecord(e->ev[3], e->stream));
+    }
+  }
+  return UML_OK;
+}
+
+static int finish_stats(uml_engine* e, uml_stats* stats, int64_t n_rows, int launches, int path, bool timed,
+                        bool kernel_events = true) {
+  // counters -> pinned mirror, then synchronise and report
+  UML_CUDA(e, cudaMemcpyAsync(&e->h->flag_count, e->d_flag_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  UML_CUDA(e, cudaMemcpyAsync(e->h->counters, e->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              e->stream));
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[4], e->stream));
+  UML_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (stats) {
+    stats->n_rows = n_rows;
+    stats->n_ambiguous = (int64_t)e->h->counters[0];
+    stats->n_nonfinite = (int64_t)e->h->counters[1];
+    stats->n_flagged = (int64_t)e->h->counters[2];
+    stats->kernel_launches = launches;
+    stats->path = path;
+    if (timed) {
+      float ms = 0.f;
+      if (kernel_events) {
+        if (cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]) == cudaSuccess) stats->kernel_ms = ms;
+        if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]) == cudaSuccess) stats->recheck_ms = ms;
+      }
+      if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]) == cudaSuccess) stats->total_ms = ms;
+      (void)cudaGetLastError();  // never leave a stale error behind for the next launch check
+    }
+  }
+  if (e->h->counters[1] > 0) UML_FAIL(e, UML_ERR_NONFINITE, "Input X contains NaN or infinity.");
+  return UML_OK;
+}
+
+static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
+                          int labels_on_device, int32_t* const* peers, int n_peers, int64_t row_offset, int mode,
+                          uml_stats* stats) {
+  if (!e || !m || !b) return UML_ERR_INVALID;
+  if (!labels_out && b->n_rows > 0 && n_peers == 0) return UML_ERR_INVALID;
+  if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
+  if (n_peers < 0 || n_peers > 8) UML_FAIL(e, UML_ERR_INVALID, "n_peers %d (max 8)", n_peers);
+  if (b->n_features != m->n_features_in)
+    UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.",
+             b->n_features, m->n_features_in);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  (void)cudaGetLastError();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (b->n_rows == 0) return UML_OK;
+  const bool exact = mode == UML_PREDICT_EXACT;
+  const bool timed = stats != nullptr;
+  int rc;
+  if (exact && (rc = ensure_flags(e, b->n_rows)) != UML_OK) return rc;
+  int32_t* d_labels = labels_out;
+  if (!labels_on_device || !labels_out) {
+    if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
+    d_labels = e->d_labels;
+  }
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], e->stream));
+  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
+  UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  LinearLaunch l{};
+  l.x = b->x;
+  l.x64 = b->x64;
+  l.ld = b->ld;
+  l.ld64 = b->ld64;
+  l.n_rows = b->n_rows;
+  l.labels = d_labels;
+  l.n_peers = n_peers;
+  for (int i = 0; i < n_peers; ++i) l.peers[i] = peers[i];
+  l.row_offset = row_offset;
+  int launches = 0, path = 0;
+  rc = enqueue_predict(e, m, l, b->has_map ? &b->map : nullptr, mode, timed, &launches, &path);
+  if (rc != UML_OK) return rc;
+  int64_t d2h = 0;
+  if (!labels_on_device && labels_out) {
+    UML_CUDA(e, cudaMemcpyAsync(labels_out, d_labels, (size_t)b->n_rows * 4, cudaMemcpyDeviceToHost, e->stream));
+    d2h = b->n_rows * 4;
+  }
+  if (stats || !labels_on_device) {
+    rc = finish_stats(e, stats, b->n_rows, launches, path, timed);
+    if (stats) {
+      stats->d2h_bytes = d2h;
+    }
+    return rc;
+  }
+  return UML_OK;
+}
+
+int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
+                       int labels_on_device, int mode, uml_stats* stats) {
+  return predict_common(e, m, b, labels_out, labels_on_device, nullptr, 0, 0, mode, stats);
+}
+
+int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* const* peer_labels,
+                             int n_peers, int64_t row_offset, int mode, uml_stats* stats) {
+  if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
+  // the first peer pointer doubles as the "local" label vector: labels land at peer[i] + row_offset for every i
+  return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, mode, stats);
+}
+
+int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
+                            int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                            int mode, int64_t chunk_rows, uml_stats* stats) {
+  if (!e || !m || (!host_ptr && n_rows > 0) || (!labels_out && n_rows > 0) || n_rows < 0 || n_features < 1)
+    return UML_ERR_INVALID;
+  if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
+  if (n_features != m->n_features_in)
+    UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.", n_features,
+             m->n_features_in);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  (void)cudaGetLastError();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_rows == 0) return UML_OK;
+  SrcLayout L{};
+  int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
+  if (rc != UML_OK) return rc;
+  const int F = n_features;
+  const int64_t ld = (F + 3) / 4 * 4;
+  const bool exact = mode == UML_PREDICT_EXACT;
+  const int64_t row_bytes = (int64_t)F * L.elem;
+  if (chunk_rows <= 0) chunk_rows = std::max<int64_t>(4096, (32ll << 20) / (ld * 4));
+  chunk_rows = std::min<int64_t>((chunk_rows + 127) / 128 * 128, (n_rows + 127) / 128 * 128);
+  const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld;
+
+  if (!direct && (rc = ensure_chunks(e, chunk_rows * row_bytes)) != UML_OK) return rc;
+  if (e->xchunk_cap < chunk_rows * ld) {
+    for (auto& p : e->d_xchunk) {
+      cudaFree(p);
+      p = nullptr;
+    }
+    e->xchunk_cap = 0;
+    for (auto& p : e->d_xchunk) UML_CUDA(e, cudaMalloc((void**)&p, (size_t)chunk_rows * ld * 4));
+    e->xchunk_cap = chunk_rows * ld;
+  }
+  if ((rc = ensure_labels(e, 3 * chunk_rows)) != UML_OK) return rc;
+  if (exact && (rc = ensure_flags(e, chunk_rows)) != UML_OK) return rc;
+
+  const bool timed = stats != nullptr;
+  cudaStream_t cs = e->stream;
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], cs));
+  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), cs));
+  UML_CUDA(e, cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), cs));
+  UML_CUDA(e, cudaEventRecord(e->chunk_ev[6], cs));
+  UML_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[6], 0));
+  int launches = 0, path = 0;
+  int64_t h2d = 0, d2h = 0;
+  bool used[3] = {false, false, false};
+  int slot = 0;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
+    const int64_t rows = std::min(chunk_rows, n_rows - r0);
+    float* xc = e->d_xchunk[slot];
+    // (1) H2D on the copy stream, once the previous user of this slot has finished scoring
+    if (used[slot]) UML_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));
+    if (direct) {
+      UML_CUDA(e, cudaMemcpyAsync(xc, (const char*)host_ptr + (size_t)r0 * ld * 4, (size_t)rows * ld * 4,
+                                  cudaMemcpyHostToDevice, e->copy_stream));
+    } else {
+      UML_CUDA(e, copy_chunk_h2d(e->d_chunk[slot], host_ptr, L, r0, rows, F, e->copy_stream));
+    }
+    h2d += rows * row_bytes;
+    UML_CUDA(e, cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
+    UML_CUDA(e, cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
+    // (2) transpose / down-cast (+ finiteness) on the compute stream
+    if (!direct) {
+      UML_CUDA(e, uml::launch_stage_convert(e->d_chunk[slot], src_dtype, L.feature_major, L.feature_major ? rows : F,
+                                            rows, F, xc, ld, nullptr, 0, e->d_stage, true, cs));
+      launches += 1;
+    } else if (!exact) {
+      UML_CUDA(e, uml::launch_finite_scan(xc, ld, rows, F, e->d_stage, cs));
+      launches += 1;
+    }
+    // (3) score
+    CUtensorMap map;
+    bool has_map = encode_map(e, &map, xc, rows, F, ld) == UML_OK;
+    LinearLaunch l{};
+    l.x = xc;
+    l.ld = ld;
+    l.n_rows = rows;
+    l.labels = e->d_labels + (int64_t)slot * chunk_rows;
+    rc = enqueue_predict(e, m, l, has_map ? &map : nullptr, mode, false, &launches, &path);
+    if (rc != UML_OK) {
+      cudaStreamSynchronize(cs);
+      cudaStreamSynchronize(e->copy_stream);
+      return rc;
+    }
+    // (4) labels back
+    UML_CUDA(e, cudaMemcpyAsync(labels_out + r0, l.labels, (size_t)rows * 4, cudaMemcpyDeviceToHost, cs));
+    d2h += rows * 4;
+    UML_CUDA(e, cudaEventRecord(e->chunk_ev[3 + slot], cs));
+    used[slot] = true;
+  }
+  UML_CUDA(e, cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
+  rc = finish_stats(e, stats, n_rows, launches, path, timed, false);
+  if (stats) {
+    stats->h2d_bytes = h2d;
+    stats->d2h_bytes = d2h;
+  }
+  if (rc == UML_OK && e->h->stage.nonfinite) UML_FAIL(e, UML_ERR_NONFINITE, "Input X contains NaN or infinity.");
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MLP (implemented in mlp_kernels.cu once the linear path is measured)
+// ---------------------------------------------------------------------------------------------------------------
+int uml_mlp_load(uml_engine* e, uml_mlp** out, const float*, const float*, const float*, const float*, int, int, int) {
+  if (out) *out = nullptr;
+  UML_FAIL(e, UML_ERR_UNSUPPORTED, "uml_mlp_load: MLP predictor not built yet");
+}
+void uml_mlp_free(uml_mlp* m) { delete m; }
+int uml_mlp_predict(uml_engine* e, const uml_mlp*, const uml_batch*, int32_t*, int, int, uml_stats*) {
+  UML_FAIL(e, UML_ERR_UNSUPPORTED, "uml_mlp_predict: MLP predictor not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+// Scoring kernels for the linear predictor  X . W^T + b -> argmax   (sm_100a).
+//
+// Replaces the numeric body of sklearn's LinearClassifierMixin.predict (sklearn/linear_model/_base.py:366-427), which
+// is what the reference's canonical predictor runs (/root/reference/README.md:87-92).
+//
+//  * linear_argmax_tma_kernel<C, EXACT>: persistent, warp-specialised.  One producer warp streams 128-row x 32-feature
+//    boxes of X (16 KiB, 128B-swizzled) through a shared-memory ring with TMA + mbarriers; eight consumer warps each
+//    own one 128-row tile at a time (4 rows per lane), read X with conflict-free LDS.128, W as warp-uniform broadcast
+//    LDS.128 from a transposed copy in shared memory, keep C (+1) fp32 accumulators per row in registers, and fuse
+//    bias, argmax (first maximum wins, like np.argmax) and the label store.  In EXACT mode one extra accumulator
+//    carries A = max|b| + sum_f |x_f| * max_c |w_cf|; rows whose top-2 margin is not provably larger than the fp32
+//    rounding error (2 (F+4) 2^-24 A) are appended to a list and re-scored in fp64 by rescore_f64_kernel.
+//  * rescore_f64_kernel: warp per row, lanes over features, fp64 FMA + shuffle reduction; serves the flagged rows of
+//    EXACT mode and is the generic (any F, any C) path when the tile kernel's shape limits do not hold.
+#include <algorithm>
+#include <cstdio>
+
+#include "uml_common.cuh"
+
+namespace uml {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// 2-D tiled bulk tensor load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA fp32 tile kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct TmaKernelParams {
+  const float* wt;    // [f_pad][CP]
+  const float* bias;  // [CP]
+  int32_t* labels;
+  int32_t* peers[8];
+  int n_peers;
+  long long row_offset;
+  long long n_rows;
+  long long num_tiles;
+  int f_pad;
+  int kc;          // 32-feature chunks per tile
+  int num_stages;  // ring depth
+  float thr;       // relative margin threshold 2 (F+4) 2^-24 (1 + slack)
+  int* flag_count;
+  int32_t* flag_rows;
+  int flag_cap;
+};
+
+template <int C, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKernelParams p) {
+  constexpr int NCOL = C + (EXACT ? 1 : 0);  // accumulators per row (classes + error-bound column)
+  constexpr int CP = (C + 1 + 3) / 4 * 4;    // padded columns of wt in shared memory (layout shared by both modes)
+  constexpr int NW4 = (NCOL + 3) / 4;        // float4 loads of W per feature
+  constexpr int R = kRowsPerLane;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1 KiB alignment
+
+  const int S = p.num_stages;
+  float* wt_s = reinterpret_cast<float*>(smem + static_cast<size_t>(S) * kStageBytes);
+  float* bias_s = wt_s + p.f_pad * CP;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + CP);
+  uint64_t* empty_bar = full_bar + S;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // stage W^T (with its wmax column) and the bias once per CTA; they stay resident for every tile this CTA scores
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.wt);
+    float4* dst = reinterpret_cast<float4*>(wt_s);
+    const int n4 = p.f_pad * CP / 4;
+    for (int i = threadIdx.x; i < n4; i += kThreads) dst[i] = __ldg(src + i);
+    if (threadIdx.x < CP) bias_s[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long G = gridDim.x;
+  const long long num_tiles = p.num_tiles;
+  const int KC = p.kc;
+
+  // Work items of this CTA, in ring order: for each round (kConsumerWarps tiles), for each 32-feature chunk k, for
+  // each active warp w: (tile = first + w*G, chunk k).  Producer and consumers derive the same sequence numbers.
+  if (warp == kConsumerWarps) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&xmap);
+      const uint64_t policy = make_evict_first_policy();  // X is read exactly once
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long first = blockIdx.x; first < num_tiles; first += G * kConsumerWarps) {
+        const int nv = static_cast<int>(min(static_cast<long long>(kConsumerWarps), (num_tiles - first + G - 1) / G));
+        for (int k = 0; k < KC; ++k) {
+          for (int w = 0; w < nv; ++w) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(smem + static_cast<size_t>(stage) * kStageBytes, &xmap, &full_bar[stage], k * kChunkF,
+                        static_cast<int>((first + w * G) * kTileRows), policy);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== consumers: one 128-row tile per warp at a time =====================
+    // lane l owns rows l, l+32, l+64, l+96 of the tile.  Row r of a box sits at byte r*128 with its 16-byte chunks
+    // XOR-swizzled by (r & 7); r & 7 == l & 7 for all four rows, so one swizzle term serves them all and the eight
+    // lanes of every LDS.128 phase hit eight distinct bank groups.
+    const uint32_t lanebase = static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>(lane & 7) * 16u;
+    uint32_t seq_base = 0;
+    for (long long first = blockIdx.x; first < num_tiles; first += G * kConsumerWarps) {
+      const int nv = static_cast<int>(min(static_cast<long long>(kConsumerWarps), (num_tiles - first + G - 1) / G));
+      if (warp < nv) {
+        const long long tile = first + warp * G;
+        float acc[R][NCOL];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) acc[j][c] = bias_s[c];
+
+        for (int k = 0; k < KC; ++k) {
+          const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + warp);
+          const uint32_t stage = seq % static_cast<uint32_t>(S);
+          const uint32_t phase = (seq / static_cast<uint32_t>(S)) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+
+          const uint8_t* xs = smem + static_cast<size_t>(stage) * kStageBytes;
+          const float* wk = wt_s + k * kChunkF * CP;
+#pragma unroll
+          for (int q = 0; q < kChunkF / 4; ++q) {
+            float4 xv[R];
+            const uint32_t off = lanebase ^ static_cast<uint32_t>(q * 16);
+#pragma unroll
+            for (int j = 0; j < R; ++j) xv[j] = *reinterpret_cast<const float4*>(xs + off + j * 32 * 128);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float wv[NW4 * 4];
+#pragma unroll
+              for (int m = 0; m < NW4; ++m) {
+                const float4 t = *reinterpret_cast<const float4*>(wk + (q * 4 + e) * CP + m * 4);
+                wv[m * 4 + 0] = t.x;
+                wv[m * 4 + 1] = t.y;
+                wv[m * 4 + 2] = t.z;
+                wv[m * 4 + 3] = t.w;
+              }
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                const float x = e == 0 ? xv[j].x : e == 1 ? xv[j].y : e == 2 ? xv[j].z : xv[j].w;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[j][c] = fmaf(x, wv[c], acc[j][c]);
+                if (EXACT) acc[j][C] = fmaf(fabsf(x), wv[C], acc[j][C]);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);  // hand the stage back to the producer
+        }
+
+        // ---- fused epilogue: argmax (first maximum wins), margin guard, label store (+ peer stores) ----
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const long long row = tile * kTileRows + lane + 32 * j;
+          float best = acc[j][0];
+          float second = -INFINITY;
+          int idx = 0;
+#pragma unroll
+          for (int c = 1; c < C; ++c) {
+            const float v = acc[j][c];
+            if (v > best) {
+              second = best;
+              best = v;
+              idx = c;
+            } else {
+              second = fmaxf(second, v);
+            }
+          }
+          const bool in_range = row < p.n_rows;
+          if (in_range) {
+            p.labels[row] = idx;
+            for (int i = 0; i < p.n_peers; ++i) p.peers[i][p.row_offset + row] = idx;
+          }
+          if (EXACT) {
+            // certain iff margin > 2 * err, err <= (F+4) 2^-24 A; NaN/Inf anywhere makes the comparison false
+            const bool certain = (best - second) > p.thr * acc[j][C];
+            const bool flagged = in_range && !certain;
+            const unsigned mask = __ballot_sync(0xffffffffu, flagged);
+            if (mask != 0u) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(p.flag_count, __popc(mask));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (flagged) {
+                const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
+              }
+            }
+          }
+        }
+      }
+      seq_base += static_cast<uint32_t>(KC * nv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp64 re-score / generic kernel: warp per row, lanes over features
+// ---------------------------------------------------------------------------------------------------------------
+struct RescoreParams {
+  const float* x;
+  const double* x64;
+  long long ld, ld64;
+  long long n_rows;
+  const double* w64;
+  const double* b64;
+  int n_classes, n_features;
+  const int* flag_count;
+  const int32_t* flag_rows;
+  int flag_cap;
+  int all_rows;
+  int32_t* labels;
+  int32_t* peers[8];
+  int n_peers;
+  long long row_offset;
+  unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] flagged (re-scored) rows
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
+  const int F = p.n_features, C = p.n_classes;
+  const double u = 1.1102230246251565e-16;  // 2^-53
+  if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
+
+  for (long long i = warp_global; i < n; i += warps_total) {
+    const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
+    const float* xr = p.x + row * p.ld;
+    const double* xr64 = p.x64 ? p.x64 + row * p.ld64 : nullptr;
+    bool bad = false;
+    double best = 0.0, second = -INFINITY, amax = 0.0;
+    int idx = 0;
+    for (int c = 0; c < C; ++c) {
+      const double* wc = p.w64 + static_cast<long long>(c) * F;
+      double s = 0.0, a = 0.0;
+      for (int f = lane; f < F; f += 32) {
+        const double xv = xr64 ? xr64[f] : static_cast<double>(xr[f]);
+        if (c == 0 && !isfinite(xv)) bad = true;
+        const double w = wc[f];
+        s = fma(xv, w, s);
+        a = fma(fabs(xv), fabs(w), a);
+      }
+      s = warp_sum(s) + p.b64[c];
+      a = warp_sum(a) + fabs(p.b64[c]);
+      amax = fmax(amax, a);
+      if (c == 0) {
+        best = s;
+      } else if (s > best) {
+        second = best;
+        best = s;
+        idx = c;
+      } else {
+        second = fmax(second, s);
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      p.labels[row] = idx;
+      for (int q = 0; q < p.n_peers; ++q) p.peers[q][p.row_offset + row] = idx;
+      if (bad) atomicAdd(&p.counters[1], 1ull);
+      // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
+      const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
+      if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static size_t tma_fixed_smem(const LinearDeviceModel& m) {
+  // alignment slack + W^T + bias + barriers (64 stages max)
+  return 1024 + static_cast<size_t>(m.f_pad) * m.cp * 4 + static_cast<size_t>(m.cp) * 4 + 2 * 64 * 8;
+}
+
+bool linear_tma_supported(const LinearDeviceModel& m, std::string* why) {
+  if (m.n_classes < 2 || m.n_classes > kMaxClassesTma) {
+    if (why) *why = "n_classes outside [2,16] for the register-tiled kernel";
+    return false;
+  }
+  if (tma_fixed_smem(m) + 4 * static_cast<size_t>(kStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
+    if (why) *why = "W^T does not fit in shared memory next to a 4-stage ring";
+    return false;
+  }
+  return true;
+}
+
+template <int C, bool EXACT>
+static cudaError_t launch_one(const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
+                              cudaStream_t stream) {
+  auto kern = linear_argmax_tma_kernel<C, EXACT>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  kern<<<grid, kThreads, smem, stream>>>(xmap, p);
+  return cudaGetLastError();
+}
+
+template <bool EXACT>
+static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
+                                    cudaStream_t stream) {
+  switch (C) {
+#define UML_CASE(N) \
+  case N:           \
+    return launch_one<N, EXACT>(xmap, p, grid, smem, stream);
+    UML_CASE(2) UML_CASE(3) UML_CASE(4) UML_CASE(5) UML_CASE(6) UML_CASE(7) UML_CASE(8) UML_CASE(9) UML_CASE(10)
+    UML_CASE(11) UML_CASE(12) UML_CASE(13) UML_CASE(14) UML_CASE(15) UML_CASE(16)
+#undef UML_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
+                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err) {
+  if (!linear_tma_supported(m, err)) return cudaErrorInvalidValue;
+  if (l.n_rows <= 0) return cudaSuccess;
+  TmaKernelParams p{};
+  p.wt = m.wt;
+  p.bias = m.bias;
+  p.labels = l.labels;
+  p.n_peers = l.n_peers;
+  for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
+  p.row_offset = l.row_offset;
+  p.n_rows = l.n_rows;
+  p.num_tiles = (l.n_rows + kTileRows - 1) / kTileRows;
+  p.f_pad = m.f_pad;
+  p.kc = m.f_pad / kChunkF;
+  const size_t fixed = tma_fixed_smem(m);
+  int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kStageBytes);
+  stages = std::min(stages, 64);
+  p.num_stages = stages;
+  // margin > 2 err guarantees the fp32 argmax is the exact argmax; err <= (F+4) 2^-24 A (1 + F 2^-21), see DESIGN.md
+  const double F = static_cast<double>(m.n_features);
+  p.thr = static_cast<float>(2.0 * (F + 4.0) * 5.9604644775390625e-08 * (1.0 + F * 4.76837158203125e-07) * 1.0001);
+  p.flag_count = flags.count;
+  p.flag_rows = flags.rows;
+  p.flag_cap = flags.capacity;
+  const size_t smem = fixed + static_cast<size_t>(stages) * kStageBytes;
+  const long long slots = (p.num_tiles + kConsumerWarps - 1) / kConsumerWarps;
+  const int grid = static_cast<int>(std::min<long long>(sm_count, std::max<long long>(1, slots)));
+  return exact ? dispatch_classes<true>(m.n_classes, xmap, p, grid, smem, stream)
+               : dispatch_classes<false>(m.n_classes, xmap, p, grid, smem, stream);
+}
+
+cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,
+                               int sm_count, cudaStream_t stream) {
+  if (l.n_rows <= 0) return cudaSuccess;
+  RescoreParams p{};
+  p.x = l.x;
+  p.x64 = l.x64;
+  p.ld = l.ld;
+  p.ld64 = l.ld64;
+  p.n_rows = l.n_rows;
+  p.w64 = m.w64;
+  p.b64 = m.b64;
+  p.n_classes = m.n_classes;
+  p.n_features = m.n_features;
+  p.flag_count = flags.count;
+  p.flag_rows = flags.rows;
+  p.flag_cap = flags.capacity;
+  p.all_rows = all_rows ? 1 : 0;
+  p.labels = l.labels;
+  p.n_peers = l.n_peers;
+  for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
+  p.row_offset = l.row_offset;
+  p.counters = flags.counters;
+  long long blocks = static_cast<long long>(sm_count) * 8;
+  if (all_rows) blocks = std::min<long long>(blocks, (l.n_rows + 7) / 8);
+  rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace uml

@@ -1,0 +1,155 @@
+// Staging kernels: feature rows in the caller's dtype/order (already copied to a device scratch chunk) -> the
+// engine's resident layout: fp32 row-major [rows][ld] (optionally also an fp64 row-major copy for exact re-scoring).
+//
+// Replaces the host-side pandas/numpy copies of Dataset.get_features (/root/reference/unionml/dataset.py:350-359,
+// 506-520: pd.DataFrame(features)[cols]) and sklearn's check_array finiteness scan
+// (sklearn/utils/validation.py:107): the scan for NaN/Inf and the "is the fp32 copy lossless" test are fused into
+// the conversion pass, so each element is touched once.
+#include "uml_common.cuh"
+
+namespace uml {
+
+template <typename T>
+__device__ __forceinline__ double load_as_double(const T* p) {
+  return static_cast<double>(*p);
+}
+
+template <typename T>
+__device__ __forceinline__ void convert_one(T v, float* out32, double* out64, unsigned& nonfinite, unsigned& lossy) {
+  const double d = static_cast<double>(v);
+  const float f = static_cast<float>(d);
+  *out32 = f;
+  if (out64) *out64 = d;
+  if (!isfinite(d)) {
+    nonfinite = 1u;
+  } else if (static_cast<double>(f) != d) {
+    lossy = 1u;
+  }
+}
+
+// source is row-major: element (r, f) at src[r * pitch + f]
+template <typename T>
+__global__ void __launch_bounds__(256) stage_rowmajor_kernel(const T* __restrict__ src, long long pitch, long long rows,
+                                                             int F, float* __restrict__ dst, long long ld,
+                                                             double* __restrict__ dst64, long long ld64,
+                                                             StageResult* result) {
+  unsigned nonfinite = 0, lossy = 0;
+  const long long total = rows * static_cast<long long>(ld);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / ld;
+    const int f = static_cast<int>(i - r * ld);
+    if (f < F) {
+      convert_one(src[r * pitch + f], dst + i, dst64 ? dst64 + r * ld64 + f : nullptr, nonfinite, lossy);
+    } else {
+      dst[i] = 0.f;  // padding columns up to ld
+    }
+  }
+  if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
+  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) atomicAdd(&result->lossy, 1ull);
+}
+
+// source is feature-major (a pandas block): element (r, f) at src[f * pitch + r]; 32x32 tiles through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) stage_featmajor_kernel(const T* __restrict__ src, long long pitch,
+                                                              long long rows, int F, float* __restrict__ dst,
+                                                              long long ld, double* __restrict__ dst64, long long ld64,
+                                                              StageResult* result) {
+  __shared__ double tile[32][33];
+  unsigned nonfinite = 0, lossy = 0;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const long long row_tiles = (rows + 31) / 32;
+  const int feat_tiles = static_cast<int>((ld + 31) / 32);
+  const long long tiles = row_tiles * feat_tiles;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long r0 = (t / feat_tiles) * 32;
+    const int f0 = static_cast<int>(t % feat_tiles) * 32;
+    // read: lanes along rows (contiguous in the source)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int f = f0 + ty + 8 * k;
+      const long long r = r0 + tx;
+      tile[ty + 8 * k][tx] = (f < F && r < rows) ? static_cast<double>(src[static_cast<long long>(f) * pitch + r]) : 0.0;
+    }
+    __syncthreads();
+    // write: lanes along features (contiguous in the destination)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long r = r0 + ty + 8 * k;
+      const int f = f0 + tx;
+      if (r < rows && f < ld) {
+        const double d = tile[tx][ty + 8 * k];
+        if (f < F) {
+          convert_one(d, dst + r * ld + f, dst64 ? dst64 + r * ld64 + f : nullptr, nonfinite, lossy);
+        } else {
+          dst[r * ld + f] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
+  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) atomicAdd(&result->lossy, 1ull);
+}
+
+// finiteness scan of rows that are already fp32 row-major on the device (no conversion needed)
+__global__ void __launch_bounds__(256) finite_scan_kernel(const float* __restrict__ x, long long ld, long long rows,
+                                                          int F, StageResult* result) {
+  unsigned nonfinite = 0;
+  const long long total = rows * static_cast<long long>(ld);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>(i % ld);
+    if (f < F && !isfinite(x[i])) nonfinite = 1u;
+  }
+  if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
+}
+
+template <typename T>
+static cudaError_t launch_typed(const void* src, bool feature_major, long long pitch, long long rows, int F, float* dst,
+                                long long ld, double* dst64, long long ld64, StageResult* result, cudaStream_t stream) {
+  const T* s = static_cast<const T*>(src);
+  if (feature_major) {
+    const long long tiles = ((rows + 31) / 32) * ((ld + 31) / 32);
+    const int grid = static_cast<int>(tiles < 148 * 16 ? (tiles < 1 ? 1 : tiles) : 148 * 16);
+    stage_featmajor_kernel<T><<<grid, 256, 0, stream>>>(s, pitch, rows, F, dst, ld, dst64, ld64, result);
+  } else {
+    const long long total = rows * ld;
+    const long long want = (total + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+    stage_rowmajor_kernel<T><<<grid, 256, 0, stream>>>(s, pitch, rows, F, dst, ld, dst64, ld64, result);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stage_convert(const void* src, int src_dtype, bool feature_major, int64_t src_pitch_elems,
+                                 int64_t rows, int n_features, float* dst, int64_t ld, double* dst64, int64_t ld64,
+                                 StageResult* result, bool check_finite, cudaStream_t stream) {
+  (void)check_finite;  // the check is fused and free; the caller decides whether to act on the counter
+  if (rows <= 0) return cudaSuccess;
+  switch (src_dtype) {
+    case UML_F32:
+      return launch_typed<float>(src, feature_major, src_pitch_elems, rows, n_features, dst, ld, dst64, ld64, result, stream);
+    case UML_F64:
+      return launch_typed<double>(src, feature_major, src_pitch_elems, rows, n_features, dst, ld, dst64, ld64, result, stream);
+    case UML_I64:
+      return launch_typed<long long>(src, feature_major, src_pitch_elems, rows, n_features, dst, ld, dst64, ld64, result, stream);
+    case UML_I32:
+      return launch_typed<int>(src, feature_major, src_pitch_elems, rows, n_features, dst, ld, dst64, ld64, result, stream);
+    case UML_U8:
+      return launch_typed<unsigned char>(src, feature_major, src_pitch_elems, rows, n_features, dst, ld, dst64, ld64, result, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
+                               cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  const long long want = (rows * ld + 255) / 256;
+  const int grid = static_cast<int>(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+  finite_scan_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, n_features, result);
+  return cudaGetLastError();
+}
+
+}  // namespace uml

@@ -1,0 +1,76 @@
+// Shared declarations for the uml_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/uml_b200.h"
+
+namespace uml {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile geometry of the TMA fp32 scoring kernel (see DESIGN.md "linear_argmax_tma")
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;                            // rows per stage = TMA box height
+constexpr int kChunkF = 32;                               // features per stage = TMA box width (128 B -> SWIZZLE_128B)
+constexpr int kStageBytes = kTileRows * kChunkF * 4;      // 16 KiB
+constexpr int kConsumerWarps = 8;                         // 2 per SM sub-partition
+constexpr int kThreads = (kConsumerWarps + 1) * 32;       // + 1 TMA producer warp
+constexpr int kRowsPerLane = kTileRows / 32;              // R = 4 rows per thread
+constexpr int kMaxClassesTma = 16;                        // classes handled in registers by the TMA kernel
+constexpr int kMaxSmemBytes = 227 * 1024;
+
+struct LinearDeviceModel {
+  // fp32 operands of the tile kernel: wt[f][cp] (feature-major, classes padded to cp = 4*ceil((C+1)/4), column C holds
+  // wmax_f = max_c |w_cf| for the error bound), bias[cp] (column C = max_c |b_c|)
+  const float* wt;
+  const float* bias;
+  // fp64 operands of the re-score / generic kernel: w64[C][F], b64[C]
+  const double* w64;
+  const double* b64;
+  int n_classes;   // C after binary expansion (>= 2)
+  int n_features;  // F
+  int cp;          // padded class columns in wt
+  int f_pad;       // rows of wt = 32 * ceil(F / 32), zero padded
+};
+
+struct FlagList {
+  int* count;        // number of flagged rows appended so far
+  int32_t* rows;     // flagged row indices
+  int capacity;
+  unsigned long long* counters;  // [0] = n_ambiguous, [1] = n_nonfinite, [2] = n_flagged
+};
+
+struct LinearLaunch {
+  const float* x;       // device fp32 row-major
+  const double* x64;    // optional fp64 copy of the same rows (lossy staging), else nullptr
+  int64_t ld;           // floats per row
+  int64_t ld64;
+  int64_t n_rows;
+  int32_t* labels;      // local label vector (device)
+  // fused all-gather epilogue: labels are also stored to peers[i] + row_offset for i < n_peers
+  int32_t* peers[8];
+  int n_peers;
+  int64_t row_offset;
+};
+
+// scoring kernels (linear_kernels.cu)
+cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
+                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err);
+bool linear_tma_supported(const LinearDeviceModel& m, std::string* why);
+cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,
+                               int sm_count, cudaStream_t stream);
+
+// staging kernels (stage_kernels.cu)
+struct StageResult {  // device-side counters
+  unsigned long long nonfinite;
+  unsigned long long lossy;
+};
+cudaError_t launch_stage_convert(const void* src, int src_dtype, bool feature_major, int64_t src_pitch_elems,
+                                 int64_t rows, int n_features, float* dst, int64_t ld, double* dst64, int64_t ld64,
+                                 StageResult* result, bool check_finite, cudaStream_t stream);
+
+}  // namespace uml

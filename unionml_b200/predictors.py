@@ -1,0 +1,96 @@
+"""Drop-in predictors for ``@model.predictor`` backed by the B200 engine.
+
+The reference's canonical predictor (``/root/reference/README.md:87-92``,
+``/root/reference/tests/integration/sklearn_app/quickstart.py:24-26``,
+``/root/reference/unionml/templates/basic/{{cookiecutter.app_name}}/app.py:26-28``) is::
+
+    @model.predictor
+    def predictor(estimator: LogisticRegression, features: pd.DataFrame) -> List[float]:
+        return [float(x) for x in estimator.predict(features)]
+
+``linear_argmax`` has the same contract (one ``features`` argument, ``List[float]`` of class labels, inputs
+borrowed and left untouched, sklearn's ``ValueError`` / ``NotFittedError`` on bad input) but computes
+``X @ coef_.T + intercept_ -> argmax -> classes_.take`` (``sklearn/linear_model/_base.py:366-427``) on the GPU.
+There is no CPU fallback: without the CUDA library or a B200 the call raises.
+"""
+
+import os
+import threading
+import weakref
+from typing import Any, List
+
+import numpy as np
+
+from unionml_b200.engine import Engine, LinearModel, get_engine
+
+_cache_lock = threading.Lock()
+_model_cache: "weakref.WeakKeyDictionary[Any, tuple]" = weakref.WeakKeyDictionary()
+
+
+def _exact_default() -> bool:
+    return os.environ.get("UNIONML_B200_MODE", "exact").lower() != "fast"
+
+
+def _check_fitted(estimator) -> None:
+    if not hasattr(estimator, "coef_") or not hasattr(estimator, "intercept_"):
+        from sklearn.exceptions import NotFittedError
+
+        raise NotFittedError(
+            f"This {type(estimator).__name__} instance is not fitted yet. Call 'fit' with appropriate arguments "
+            "before using this estimator."
+        )
+
+
+def _check_feature_names(estimator, features) -> None:
+    """sklearn validates column names *and order* on predict (``sklearn/utils/validation.py:2769``)."""
+    fitted = getattr(estimator, "feature_names_in_", None)
+    cols = getattr(features, "columns", None)
+    if fitted is None or cols is None:
+        return
+    names = np.asarray(cols, dtype=object)
+    if not all(isinstance(c, str) for c in names):
+        return
+    if len(names) != len(fitted) or np.any(names != fitted):
+        raise ValueError(
+            "The feature names should match those that were passed during fit.\n"
+            f"Feature names seen at fit time: {list(fitted)[:5]}..., passed now: {list(names)[:5]}..."
+        )
+
+
+def device_model(estimator, engine: Engine | None = None) -> LinearModel:
+    """The estimator's ``coef_``/``intercept_`` staged on the device, cached per estimator object and weights."""
+    _check_fitted(estimator)
+    engine = engine or get_engine()
+    coef = np.asarray(estimator.coef_)
+    intercept = np.asarray(estimator.intercept_)
+    key = (id(engine), coef.shape, coef.dtype.str, hash(coef.tobytes()), hash(intercept.tobytes()))
+    with _cache_lock:
+        try:
+            hit = _model_cache.get(estimator)
+        except TypeError:  # unhashable / not weak-referenceable estimator: no caching
+            hit = None
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dm = engine.load_linear(coef, intercept, getattr(estimator, "classes_", None))
+        try:
+            _model_cache[estimator] = (key, dm)
+        except TypeError:
+            pass
+        return dm
+
+
+def linear_predict_labels(estimator, features, exact: bool | None = None, engine: Engine | None = None) -> np.ndarray:
+    """``estimator.predict(features)`` on the GPU: ndarray of class labels (``classes_`` dtype)."""
+    engine = engine or get_engine()
+    dm = device_model(estimator, engine)
+    _check_feature_names(estimator, features)
+    idx, _stats = engine.predict_host(dm, features, exact=_exact_default() if exact is None else exact)
+    classes = getattr(estimator, "classes_", None)
+    if classes is None:
+        return idx.astype(np.int64)
+    return np.asarray(classes).take(idx, axis=0)
+
+
+def linear_argmax(estimator: Any, features: Any) -> List[float]:
+    """Drop-in body for ``@model.predictor``: class labels as Python floats."""
+    return linear_predict_labels(estimator, features).astype(np.float64).tolist()
