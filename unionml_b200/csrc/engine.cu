@@ -447,8 +447,9 @@ int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t
   UML_CUDA(e, cudaSetDevice(e->device));
   (void)cudaGetLastError();
   SrcLayout L{};
-  int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
-  if (rc != UML_OK) return rc;
+  int rc = UML_OK;
+  if (n_rows > 0 && (rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L)) != UML_OK)
+    return rc;
   const int F = n_features;
   const int64_t ld = (F + 3) / 4 * 4;
   const bool check = !(flags & UML_STAGE_SKIP_FINITE_CHECK);
