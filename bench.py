@@ -236,7 +236,9 @@ def workload_config(args, n_gpus: int) -> dict:
         "n_features": N_FEATURES,
         "n_classes": 10,
         "mode": "exact (fp32 tile kernel + margin guard + fp64 re-score; labels == sklearn float64 labels)",
-        "parallelism": f"row-sharded x{n_gpus}, all-gather of int32 labels" if n_gpus > 1 else "single GPU",
+        "parallelism": (f"row-sharded x{n_gpus}, label exchange: " + getattr(args, "gather_used", args.gather))
+        if n_gpus > 1
+        else "single GPU",
         "l2_policy": f"inputs ({args.rows * BYTES_PER_ROW / 1e9:.2f} GB/step) are larger than L2 (126 MB); no flush needed",
     }
 
@@ -280,19 +282,42 @@ def run_gpu_arm(args):
     labels_host = eng.pinned_empty(rows, np.int32)
 
     batch = eng.stage(X_host)  # resident fp32 row-major copy for the `value` leg
-    labels_all = torch.empty(rows * world, dtype=torch.int32, device=dev)
+    from unionml_b200.sharding import PeerLabelExchange, predict_sharded
+
+    counts = [rows] * world
+    exchange = None
+    gather = "none" if world == 1 else args.gather
+    if world > 1 and gather == "fused":
+        try:
+            exchange = PeerLabelExchange(rows * world, dev)
+        except Exception as exc:  # symmetric memory unavailable on this box: fall back to the NCCL all-gather
+            if rank == 0:
+                print(f"bench: symmetric memory unavailable ({exc!r}); using nccl all-gather", file=sys.stderr)
+            gather = "nccl"
+    labels_all = exchange.labels if exchange is not None else torch.empty(rows * world, dtype=torch.int32, device=dev)
     labels_local = labels_all[rank * rows : (rank + 1) * rows]
 
+    interleave = interleave_out = None
+    if args.interleave:
+        interleave = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
+        interleave_out = torch.empty_like(interleave)
+
     def step():
-        eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=False)
-        if world > 1:
-            dist.all_gather_into_tensor(labels_all, labels_local)
+        if world == 1:
+            eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=False)
+            if interleave is not None:  # --interleave: a foreign kernel between steps (robustness check, not a bench)
+                torch.matmul(interleave, interleave, out=interleave_out)
+        else:
+            predict_sharded(eng, model, batch, row_offset=rank * rows, counts=counts, exact=True, exchange=exchange,
+                            labels_all=labels_all)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    args.gather_used = {"fused": "fused peer stores from the kernel epilogue over NVLink (symmetric memory) + barrier",
+                        "nccl": "ncclAllGather of int32 labels", "none": "none"}[gather]
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -374,6 +399,14 @@ def run_gpu_arm(args):
         "steps": args.e2e_steps,
         "path": "Engine.predict_host: pinned fp32 rows -> chunked H2D -> linear_argmax_tma (+fp64 re-score) -> D2H int32 labels",
     }
+    if world > 1:
+        # every rank must hold every rank's labels: compare the exchanged vector with a plain NCCL all-gather
+        step()
+        ref_all = torch.empty(rows * world, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(ref_all, labels_local.clone())
+        torch.cuda.synchronize()
+        if not torch.equal(ref_all, labels_all):
+            raise SystemExit(f"bench: rank {rank}: exchanged label vector differs from the NCCL all-gather")
     # sanity: resident and streamed paths agree
     check = labels_local.cpu().numpy()
     if not np.array_equal(check, labels_host):
@@ -438,6 +471,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="bounded CPU sample (rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: skip the host-buffer leg")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="label exchange for --gpus > 1")
+    ap.add_argument("--interleave", action="store_true", help="robustness check: run a cuBLAS GEMM between steps")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from the committed ncu capture")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -128,8 +128,9 @@ UML_API void uml_batch_free(uml_batch* b);
 UML_API int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
                        int labels_on_device, int mode, uml_stats* stats);
 /* fused compute + collective: every rank's kernel epilogue stores its labels straight into all peers' label vectors
- * over NVLink (peer_labels[i] = base of rank i's full-length int32 vector, already mapped for peer access;
- * this rank's rows land at row_offset).  Replaces kernel + ncclAllGather. */
+ * over NVLink (peer_labels[0] = base of THIS rank's full-length int32 vector, peer_labels[1..] = the other ranks'
+ * vectors, already mapped for peer access; this rank's rows land at row_offset in each).  Replaces kernel +
+ * ncclAllGather; the caller still needs one cross-rank barrier before reading peers' rows. */
 UML_API int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* const* peer_labels,
                              int n_peers, int64_t row_offset, int mode, uml_stats* stats);
 /* end to end from HOST rows to HOST labels in one call (the /predict and Model.predict(features=...) shape): chunked

@@ -269,3 +269,54 @@ def test_full_size_ten_million(engine, digits_model):
     # (4) label histogram is a checksum that must agree between modes except on flagged rows
     fast, _ = engine.predict(m, b, exact=False)
     assert (fast != labels).sum() <= st["n_flagged"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ring-protocol regression: foreign kernels between launches perturb TMA completion order (cold TLB / L2).  A first
+# version of the kernel let a consumer warp run one barrier phase ahead of a stage's previous occupant and faulted
+# or hung within a few launches in exactly this setting; UML_B200_STAGES=8 is the shallowest legal ring.
+# ---------------------------------------------------------------------------------------------------------------
+_RING_WORKER = r'''
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.environ["UML_ROOT"])
+from oracle import linear as olin
+from unionml_b200.engine import Engine
+z = np.load(os.path.join(os.environ["UML_ROOT"], "tests", "golden", "digits_lr.npz"))
+dev = torch.device("cuda", 0)
+eng = Engine(0); s = torch.cuda.Stream(device=dev); torch.cuda.set_stream(s); eng.set_stream(s.cuda_stream)
+m = eng.load_linear(z["coef"], z["intercept"])
+X = np.random.default_rng(3).integers(0, 17, size=(3_000_000, 64), dtype=np.uint8).astype(np.float32)
+want = olin.predict_indices(olin.decision_function(X.astype(np.float64), z["coef"], z["intercept"])).astype(np.int32)
+b = eng.stage(X)
+out = torch.empty(X.shape[0], dtype=torch.int32, device=dev)
+a = torch.randn(2048, 2048, device=dev, dtype=torch.bfloat16); c = torch.empty_like(a); d = torch.zeros(1 << 22, device=dev)
+for i in range(60):
+    out.fill_(-1)
+    eng.predict(m, b, exact=(i % 2 == 0), out_device_ptr=out.data_ptr(), want_stats=False)
+    if i % 3 == 0: torch.matmul(a, a, out=c)
+    elif i % 3 == 1: d.add_(1)
+    else: torch.cuda._sleep(500_000)
+    if i % 10 == 0:
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert (got != want).sum() <= (0 if i % 2 == 0 else 5), i
+torch.cuda.synchronize()
+print("ring ok")
+'''
+
+
+@pytest.mark.parametrize("stages", ["", "8"])
+def test_ring_protocol_with_foreign_kernels_between_launches(tmp_path, stages):
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    script = tmp_path / "ring_worker.py"
+    script.write_text(_RING_WORKER)
+    env = dict(os.environ, UML_ROOT=str(Path(__file__).resolve().parent.parent))
+    if stages:
+        env["UML_B200_STAGES"] = stages
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ring ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -664,7 +664,12 @@ static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b,
   int rc;
   if (exact && (rc = ensure_flags(e, b->n_rows)) != UML_OK) return rc;
   int32_t* d_labels = labels_out;
-  if (!labels_on_device || !labels_out) {
+  if (!labels_out && n_peers > 0) {
+    // fused exchange: entry 0 is this rank's own full-length vector -> it is the local label target
+    d_labels = peers[0] + row_offset;
+    peers += 1;
+    n_peers -= 1;
+  } else if (!labels_on_device || !labels_out) {
     if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
     d_labels = e->d_labels;
   }
@@ -707,7 +712,7 @@ int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batch* b, in
 int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* const* peer_labels,
                              int n_peers, int64_t row_offset, int mode, uml_stats* stats) {
   if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
-  // the first peer pointer doubles as the "local" label vector: labels land at peer[i] + row_offset for every i
+  // peer_labels[0] must be this rank's own vector (local target); labels land at peer_labels[i] + row_offset for all i
   return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, mode, stats);
 }
 

@@ -14,6 +14,7 @@
 //    EXACT mode and is the generic (any F, any C) path when the tile kernel's shape limits do not hold.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "uml_common.cuh"
 
@@ -57,14 +58,24 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
-// 2-D tiled bulk tensor load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
+// 2-D tiled bulk tensor load global -> shared (own CTA), completion signalled on an mbarrier (SASS: UTMALDG)
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+// exactly one lane of a converged warp (elect.sync): lets ptxas treat the TMA operands as warp-uniform
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -132,8 +143,8 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
   // Work items of this CTA, in ring order: for each round (kConsumerWarps tiles), for each 32-feature chunk k, for
   // each active warp w: (tile = first + w*G, chunk k).  Producer and consumers derive the same sequence numbers.
   if (warp == kConsumerWarps) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (elect_one_sync()) {
       tma_prefetch_desc(&xmap);
       const uint64_t policy = make_evict_first_policy();  // X is read exactly once
       int stage = 0;
@@ -175,6 +186,14 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
           const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + warp);
           const uint32_t stage = seq % static_cast<uint32_t>(S);
           const uint32_t phase = (seq / static_cast<uint32_t>(S)) & 1u;
+          // A parity wait can only tell the current phase from the one before it.  Several warps share this ring and
+          // TMA completions are unordered, so the previous occupant of the stage (item seq - S, another warp's) may
+          // still be in flight or unread when this warp gets here; waiting on `full` right away would then match the
+          // *older* phase and read another tile's half-landed box.  First wait until that occupant has been released
+          // (empty phase seq/S - 1), then for our own data.  Both waits are at most one phase ahead of their barrier
+          // because a warp's next item is seq + nv <= seq + kConsumerWarps and the ring has S >= kConsumerWarps stages:
+          // the producer could only issue item seq after item seq - S was released, so item seq + nv - 2S was too.
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_wait(&full_bar[stage], phase);
 
           const uint8_t* xs = smem + static_cast<size_t>(stage) * kStageBytes;
@@ -346,8 +365,9 @@ bool linear_tma_supported(const LinearDeviceModel& m, std::string* why) {
     if (why) *why = "n_classes outside [2,16] for the register-tiled kernel";
     return false;
   }
-  if (tma_fixed_smem(m) + 4 * static_cast<size_t>(kStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
-    if (why) *why = "W^T does not fit in shared memory next to a 4-stage ring";
+  // the ring protocol needs at least as many stages as consumer warps (see the comment at the consumers' waits)
+  if (tma_fixed_smem(m) + kConsumerWarps * static_cast<size_t>(kStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
+    if (why) *why = "W^T does not fit in shared memory next to an 8-stage ring";
     return false;
   }
   return true;
@@ -396,6 +416,8 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
   const size_t fixed = tma_fixed_smem(m);
   int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kStageBytes);
   stages = std::min(stages, 64);
+  // test hook: the shallowest legal ring (stages == consumer warps) stresses the barrier protocol
+  if (const char* env = getenv("UML_B200_STAGES")) stages = std::max(kConsumerWarps, std::min(stages, atoi(env)));
   p.num_stages = stages;
   // margin > 2 err guarantees the fp32 argmax is the exact argmax; err <= (F+4) 2^-24 A (1 + F 2^-21), see DESIGN.md
   const double F = static_cast<double>(m.n_features);

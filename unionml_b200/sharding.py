@@ -1,0 +1,88 @@
+"""Row sharding across GPUs: one process per GPU, W/b replicated, labels exchanged once.
+
+The reference has no distributed path (scale-out = independent Flyte pods, ``/root/reference/unionml/model.py:1160-1226``);
+rows are independent, so rank r scores a contiguous row block and every rank ends up with the full label vector
+(SURVEY.md 8e).  Two exchange back-ends:
+
+* ``nccl``  - ``torch.distributed.all_gather_into_tensor`` of the int32 label vector after the kernel;
+* ``fused`` - the scoring kernel's epilogue stores each label into every peer's vector over NVLink
+  (``uml_linear_predict_peers``; peer pointers from ``torch.distributed._symmetric_memory``), followed by one
+  symmetric-memory barrier.  No separate collective kernel, no extra pass over the labels.
+
+The host-side logic (``shard_bounds``, ``gather_labels``) is backend-agnostic and covered by world_size-2 ``gloo`` tests.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of rank ``rank``; the first ``n_rows % world`` ranks hold one extra row."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_counts(n_rows: int, world: int) -> List[int]:
+    return [shard_bounds(n_rows, r, world)[1] - shard_bounds(n_rows, r, world)[0] for r in range(world)]
+
+
+def gather_labels(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """All-gather per-rank label vectors (possibly ragged) into the full vector, on whatever backend ``group`` uses."""
+    world = dist.get_world_size(group)
+    if len(counts) != world:
+        raise ValueError("counts must have one entry per rank")
+    if local.numel() != counts[dist.get_rank(group)]:
+        raise ValueError("local label vector does not match this rank's shard size")
+    if len(set(counts)) == 1:
+        out = torch.empty(sum(counts), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    width = max(counts)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    buf = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * width : r * width + counts[r]] for r in range(world)])
+
+
+class PeerLabelExchange:
+    """A full-length int32 label vector in symmetric memory on every rank + the peers' device pointers."""
+
+    def __init__(self, total_rows: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.labels = symm_mem.empty(total_rows, dtype=torch.int32, device=device)
+        self.handle = symm_mem.rendezvous(self.labels, self.group)
+        self.rank = self.handle.rank
+        self.world = self.handle.world_size
+        ptrs = list(self.handle.buffer_ptrs)
+        # own pointer first: the kernel treats entry 0 as its local label vector
+        self.peer_ptrs = [ptrs[self.rank]] + [p for r, p in enumerate(ptrs) if r != self.rank]
+
+    def barrier(self) -> None:
+        """All ranks' stores have landed everywhere (device-side barrier on the current stream)."""
+        self.handle.barrier()
+
+
+def predict_sharded(engine, model, batch, *, row_offset: int, counts: Sequence[int], exact: bool = True,
+                    exchange: Optional[PeerLabelExchange] = None, labels_all: Optional[torch.Tensor] = None,
+                    group=None) -> torch.Tensor:
+    """Score this rank's resident shard and return the full label vector (device tensor, identical on all ranks)."""
+    rank = dist.get_rank(group)
+    if exchange is not None:
+        engine.predict_peers(model, batch, exchange.peer_ptrs, row_offset, exact=exact)
+        exchange.barrier()
+        return exchange.labels
+    if labels_all is None:
+        labels_all = torch.empty(sum(counts), dtype=torch.int32, device=torch.device("cuda", engine.device))
+    local = labels_all[row_offset : row_offset + counts[rank]]
+    engine.predict(model, batch, exact=exact, out_device_ptr=local.data_ptr(), want_stats=False)
+    if len(set(counts)) == 1:
+        dist.all_gather_into_tensor(labels_all, local, group=group)
+        return labels_all
+    return gather_labels(local.clone(), counts, group)
