@@ -89,3 +89,37 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_mlp_golden():
+    """PytorchModel(64, 32, 10) of tests/integration/pytorch_app/quickstart.py:14-24,80 with torch.manual_seed(0),
+    and torch's own labels on a seeded digits-domain batch (the reference predictor run as written)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class PytorchModel(nn.Module):
+        def __init__(self, in_dims: int, hidden_dims: int, out_dims: int):
+            super().__init__()
+            self.layers = nn.Sequential(nn.Linear(in_dims, hidden_dims), nn.ReLU(), nn.Linear(hidden_dims, out_dims))
+
+        def forward(self, features):
+            return F.softmax(self.layers(features), dim=1)
+
+    torch.manual_seed(0)
+    module = PytorchModel(64, 32, 10)
+    X = np.random.default_rng(2025).integers(0, 17, size=(4096, 64), dtype=np.uint8)
+    with torch.no_grad():
+        labels = module(torch.from_numpy(X.astype(np.float64)).float()).argmax(1).numpy()
+    sd = module.state_dict()
+    np.savez_compressed(
+        HERE / "mlp_64_32_10.npz",
+        w1=sd["layers.0.weight"].numpy(), b1=sd["layers.0.bias"].numpy(),
+        w2=sd["layers.2.weight"].numpy(), b2=sd["layers.2.bias"].numpy(),
+        X=X, labels_torch=labels,
+    )
+    print("wrote mlp_64_32_10.npz; label histogram", np.bincount(labels, minlength=10))
+
+
+if __name__ == "__main__" and "--mlp" in __import__("sys").argv:
+    make_mlp_golden()

@@ -147,3 +147,33 @@ def test_parser_quirk():
     spec.reader = reader
     # ...while the feature loader honours the explicit list (dataset.py:515-518)
     assert list(opath.default_feature_loader(spec, df).columns) == ["x"]
+
+
+def test_mlp_oracle_pinned_to_torch():
+    """oracle.mlp against torch itself (the reference predictor as written) and the committed fixture."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from oracle import mlp as omlp
+    from tests.conftest import GOLDEN
+
+    z = np.load(GOLDEN / "mlp_64_32_10.npz")
+    w = (z["w1"], z["b1"], z["w2"], z["b2"])
+    np.testing.assert_array_equal(omlp.predict_indices_f32(z["X"], *w), z["labels_torch"])
+    np.testing.assert_array_equal(omlp.predict_indices_f64(z["X"], *w), z["labels_torch"])
+
+    layers = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
+    with torch.no_grad():
+        layers[0].weight.copy_(torch.from_numpy(z["w1"]))
+        layers[0].bias.copy_(torch.from_numpy(z["b1"]))
+        layers[2].weight.copy_(torch.from_numpy(z["w2"]))
+        layers[2].bias.copy_(torch.from_numpy(z["b2"]))
+        X = np.random.default_rng(11).integers(0, 17, size=(50_000, 64)).astype(np.float64)
+        want = F.softmax(layers(torch.from_numpy(X).float()), dim=1).argmax(1).numpy()
+    got = omlp.predict_indices_f64(X, *w)
+    mism = np.flatnonzero(got != want)
+    assert len(mism) <= 2 and np.all(omlp.logit_margin_f64(X, *w)[mism] < 1e-4)
+    assert omlp.canonical_predictor({"w1": w[0], "b1": w[1], "w2": w[2], "b2": w[3]}, pd.DataFrame(X[:5])) == [
+        float(v) for v in want[:5]
+    ]

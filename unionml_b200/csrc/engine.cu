@@ -75,11 +75,17 @@ struct uml_batch {
   bool owns = false;
   bool lossless = true;
   bool has_map = false;
-  CUtensorMap map{};
+  CUtensorMap map{};  // boxes of 128 rows x 32 features
 };
 
 struct uml_mlp {
   uml_engine* e = nullptr;
+  uml::MlpDeviceModel dm{};
+  float* d_w1t = nullptr;
+  float* d_b1 = nullptr;
+  float* d_w2t = nullptr;
+  float* d_b2 = nullptr;
+  double* d_w64 = nullptr;  // w1 | b1 | w2 | b2 packed
 };
 
 #define UML_FAIL(E, CODE, ...)                              \
@@ -345,12 +351,13 @@ void uml_model_free(uml_model* m) {
 // ---------------------------------------------------------------------------------------------------------------
 // batch
 // ---------------------------------------------------------------------------------------------------------------
-static int encode_map(uml_engine* e, CUtensorMap* map, const float* x, int64_t n_rows, int F, int64_t ld) {
+static int encode_map(uml_engine* e, CUtensorMap* map, const float* x, int64_t n_rows, int F, int64_t ld,
+                      int box_rows = uml::kTileRows) {
   if (((uintptr_t)x & 15) != 0 || (ld % 4) != 0) UML_FAIL(e, UML_ERR_UNSUPPORTED, "rows must be 16-byte aligned with ld %% 4 == 0");
   if (n_rows >= (1ll << 31) - uml::kTileRows) UML_FAIL(e, UML_ERR_UNSUPPORTED, "more than 2^31 rows in one batch");
   cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)n_rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)uml::kChunkF, (cuuint32_t)uml::kTileRows};
+  cuuint32_t box[2] = {(cuuint32_t)uml::kChunkF, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -818,15 +825,161 @@ int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MLP (implemented in mlp_kernels.cu once the linear path is measured)
+// MLP: PytorchModel(in, hidden, out) of tests/integration/pytorch_app/quickstart.py
 // ---------------------------------------------------------------------------------------------------------------
-int uml_mlp_load(uml_engine* e, uml_mlp** out, const float*, const float*, const float*, const float*, int, int, int) {
-  if (out) *out = nullptr;
-  UML_FAIL(e, UML_ERR_UNSUPPORTED, "uml_mlp_load: MLP predictor not built yet");
+int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1, const float* w2, const float* b2,
+                 int n_in, int n_hidden, int n_out) {
+  if (!e || !out || !w1 || !b1 || !w2 || !b2) return UML_ERR_INVALID;
+  *out = nullptr;
+  if (n_in < 1 || n_hidden < 1 || n_out < 2 || n_hidden > 256)
+    UML_FAIL(e, UML_ERR_UNSUPPORTED, "MLP shape %d -> %d -> %d (need hidden <= 256, out >= 2)", n_in, n_hidden, n_out);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  const int F = n_in, H = n_hidden, C = n_out;
+  const int HP = H + 4, cp = (C + 1 + 3) / 4 * 4;
+  const int f_pad = (F + uml::kChunkF - 1) / uml::kChunkF * uml::kChunkF;
+  std::vector<float> w1t((size_t)f_pad * HP, 0.f), b1p(HP, 0.f), w2t((size_t)H * cp, 0.f), b2p(cp, 0.f);
+  for (int f = 0; f < F; ++f) {
+    float wmax = 0.f;
+    for (int n = 0; n < H; ++n) {
+      const float v = w1[(size_t)n * F + f];  // torch Linear weight: (out, in)
+      w1t[(size_t)f * HP + n] = v;
+      wmax = fmaxf(wmax, fabsf(v));
+    }
+    w1t[(size_t)f * HP + H] = wmax;
+  }
+  float bmax = 0.f;
+  for (int n = 0; n < H; ++n) {
+    b1p[n] = b1[n];
+    bmax = fmaxf(bmax, fabsf(b1[n]));
+  }
+  b1p[H] = bmax;
+  double row_sum_max = 0.0;
+  for (int c = 0; c < C; ++c) {
+    double rs = 0.0;
+    for (int n = 0; n < H; ++n) rs += fabs((double)w2[(size_t)c * H + n]);
+    row_sum_max = std::max(row_sum_max, rs);
+  }
+  for (int n = 0; n < H; ++n) {
+    float wmax = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = w2[(size_t)c * H + n];
+      w2t[(size_t)n * cp + c] = v;
+      wmax = fmaxf(wmax, fabsf(v));
+    }
+    w2t[(size_t)n * cp + C] = wmax;
+  }
+  bmax = 0.f;
+  for (int c = 0; c < C; ++c) {
+    b2p[c] = b2[c];
+    bmax = fmaxf(bmax, fabsf(b2[c]));
+  }
+  b2p[C] = bmax;
+  std::vector<double> w64((size_t)H * F + H + (size_t)C * H + C);
+  double* q = w64.data();
+  for (size_t i = 0; i < (size_t)H * F; ++i) *q++ = w1[i];
+  for (int i = 0; i < H; ++i) *q++ = b1[i];
+  for (size_t i = 0; i < (size_t)C * H; ++i) *q++ = w2[i];
+  for (int i = 0; i < C; ++i) *q++ = b2[i];
+
+  uml_mlp* m = new uml_mlp();
+  m->e = e;
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t ce = cudaMalloc(dst, bytes);
+    if (ce != cudaSuccess) return ce;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t ce;
+  if ((ce = up((void**)&m->d_w1t, w1t.data(), w1t.size() * 4)) != cudaSuccess ||
+      (ce = up((void**)&m->d_b1, b1p.data(), b1p.size() * 4)) != cudaSuccess ||
+      (ce = up((void**)&m->d_w2t, w2t.data(), w2t.size() * 4)) != cudaSuccess ||
+      (ce = up((void**)&m->d_b2, b2p.data(), b2p.size() * 4)) != cudaSuccess ||
+      (ce = up((void**)&m->d_w64, w64.data(), w64.size() * 8)) != cudaSuccess) {
+    e->last_error = std::string("uml_mlp_load: ") + cudaGetErrorString(ce);
+    uml_mlp_free(m);
+    return ce == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA;
+  }
+  m->dm.w1t = m->d_w1t;
+  m->dm.b1 = m->d_b1;
+  m->dm.w2t = m->d_w2t;
+  m->dm.b2 = m->d_b2;
+  m->dm.w1_64 = m->d_w64;
+  m->dm.b1_64 = m->d_w64 + (size_t)H * F;
+  m->dm.w2_64 = m->dm.b1_64 + H;
+  m->dm.b2_64 = m->dm.w2_64 + (size_t)C * H;
+  m->dm.n_in = F;
+  m->dm.n_hidden = H;
+  m->dm.n_classes = C;
+  m->dm.cp = cp;
+  m->dm.f_pad = f_pad;
+  m->dm.w2_abs_row_sum_max = row_sum_max;
+  *out = m;
+  return UML_OK;
 }
-void uml_mlp_free(uml_mlp* m) { delete m; }
-int uml_mlp_predict(uml_engine* e, const uml_mlp*, const uml_batch*, int32_t*, int, int, uml_stats*) {
-  UML_FAIL(e, UML_ERR_UNSUPPORTED, "uml_mlp_predict: MLP predictor not built yet");
+
+void uml_mlp_free(uml_mlp* m) {
+  if (!m) return;
+  if (m->e) cudaSetDevice(m->e->device);
+  cudaFree(m->d_w1t);
+  cudaFree(m->d_b1);
+  cudaFree(m->d_w2t);
+  cudaFree(m->d_b2);
+  cudaFree(m->d_w64);
+  delete m;
+}
+
+int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
+                    int mode, uml_stats* stats) {
+  if (!e || !m || !b || (!labels_out && b->n_rows > 0)) return UML_ERR_INVALID;
+  if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
+  if (b->n_features != m->dm.n_in)
+    UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the module is expecting %d features as input.", b->n_features,
+             m->dm.n_in);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  (void)cudaGetLastError();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (b->n_rows == 0) return UML_OK;
+  const bool exact = mode == UML_PREDICT_EXACT;
+  const bool timed = stats != nullptr;
+  int rc;
+  if (exact && (rc = ensure_flags(e, b->n_rows)) != UML_OK) return rc;
+  int32_t* d_labels = labels_out;
+  if (!labels_on_device) {
+    if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
+    d_labels = e->d_labels;
+  }
+  FlagList fl{e->d_flag_count, e->d_flag_rows, (int)std::min<int64_t>(e->flag_cap, INT32_MAX), e->d_counters};
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], e->stream));
+  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
+  UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  int launches = 0, path = 3;
+  std::string why;
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[1], e->stream));
+  if (b->has_map && uml::mlp_tma_supported(m->dm, &why)) {
+    UML_CUDA(e, uml::launch_mlp_tma(b->map, m->dm, b->x, b->n_rows, d_labels, exact, fl, e->info.sm_count, e->stream));
+    launches += 1;
+    if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
+    if (exact) {
+      UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, d_labels, fl, false, e->info.sm_count, e->stream));
+      launches += 1;
+    }
+  } else {
+    UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, d_labels, fl, true, e->info.sm_count, e->stream));
+    launches += 1;
+    path = 2;
+    if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
+  }
+  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[3], e->stream));
+  int64_t d2h = 0;
+  if (!labels_on_device) {
+    UML_CUDA(e, cudaMemcpyAsync(labels_out, d_labels, (size_t)b->n_rows * 4, cudaMemcpyDeviceToHost, e->stream));
+    d2h = b->n_rows * 4;
+  }
+  if (stats || !labels_on_device) {
+    rc = finish_stats(e, stats, b->n_rows, launches, path, timed);
+    if (stats) stats->d2h_bytes = d2h;
+    return rc;
+  }
+  return UML_OK;
 }
 
 }  // extern "C"

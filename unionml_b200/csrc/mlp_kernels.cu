@@ -1,0 +1,424 @@
+// Scoring kernels for the 2-layer MLP predictor  argmax(softmax(W2 relu(W1 x + b1) + b2)) = argmax of the logits.
+//
+// Replaces PytorchModel.forward + .argmax(1) of the reference's torch quickstart
+// (/root/reference/tests/integration/pytorch_app/quickstart.py:14-24, 68-70; hyperparameters 64 -> 32 -> 10 at :80).
+//
+//  * mlp_argmax_tma_kernel<H, C, EXACT>: the same persistent TMA + mbarrier ring (128-row x 32-feature boxes) as the
+//    linear kernel, but 4 consumer warps per CTA so a lane can carry H hidden accumulators for each of its 4 rows.  Layer 1 runs per
+//    landed box (W1^T rows are warp-uniform broadcast LDS.128 from shared memory), then ReLU, layer 2 and the argmax are
+//    fused in registers.  EXACT mode carries two bound accumulators (A1 over layer 1, A2 over layer 2) and re-scores
+//    rows whose logit margin is inside the propagated fp32 error bound in fp64.
+//  * mlp_rescore_f64_kernel: warp per row, lane per hidden unit, fp64; flagged rows of EXACT mode, or every row for
+//    shapes the tile kernel is not instantiated for.
+//
+// This is CUDA-core fp32 (FFMA): 4 736 flop/row puts the HBM roofline (25 G rows/s) above the FFMA peak, so this kernel
+// is FMA-pipe bound (~0.66 ms per 10M rows at 1.9 GHz); a tcgen05 TF32x3 layer 1 is the planned next step.
+#include <algorithm>
+#include <cstdlib>
+
+#include "uml_common.cuh"
+#include "tma_ring.cuh"
+
+namespace uml {
+
+// 4 consumer warps (one per SM sub-partition) + 1 producer warp = 160 threads: with 5 warps per CTA a thread may hold up
+// to 255 registers, which is what 4 rows x 32 hidden accumulators per lane need (9 warps would cap it at 168).
+constexpr int kMlpConsumerWarps = 4;
+constexpr int kMlpThreads = (kMlpConsumerWarps + 1) * 32;
+constexpr int kMlpTileRows = kTileRows;                      // 128 rows x 32 features, same boxes as the linear kernel
+constexpr int kMlpStageBytes = kStageBytes;                  // 16 KiB
+constexpr int kMlpRowsPerLane = kMlpTileRows / 32;           // 4
+
+struct MlpKernelParams {
+  const float* w1t;  // [f_pad][H + 4]   column H = max_n |w1_nf|
+  const float* b1;   // [H + 4]          entry  H = max_n |b1_n|
+  const float* w2t;  // [H][CP]          column C = max_c |w2_cn|
+  const float* b2;   // [CP]             entry  C = max_c |b2_c|
+  int32_t* labels;
+  long long n_rows;
+  long long num_tiles;
+  int f_pad;
+  int kc;
+  int num_stages;
+  float e1_scale;  // (F+4) 2^-24 (1+slack) * max_c sum_n |w2_cn|   -> layer-1 error as it reaches a logit
+  float e2_scale;  // (H+4) 2^-24 (1+slack)                          -> layer-2 accumulation error
+  int* flag_count;
+  int32_t* flag_rows;
+  int flag_cap;
+};
+
+template <int H, int C, bool EXACT>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelParams p) {
+  constexpr int HP = H + 4;
+  constexpr int CP = (C + 1 + 3) / 4 * 4;
+  constexpr int NC2 = C + (EXACT ? 1 : 0);
+  constexpr int NW2 = (NC2 + 3) / 4;
+  constexpr int R = kMlpRowsPerLane;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = p.num_stages;
+  float* w1_s = reinterpret_cast<float*>(smem + static_cast<size_t>(S) * kMlpStageBytes);
+  float* b1_s = w1_s + p.f_pad * HP;
+  float* w2_s = b1_s + HP;
+  float* b2_s = w2_s + H * CP;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b2_s + CP);
+  uint64_t* empty_bar = full_bar + S;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.w1t);
+    float4* dst = reinterpret_cast<float4*>(w1_s);
+    for (int i = threadIdx.x; i < p.f_pad * HP / 4; i += kMlpThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < H * CP; i += kMlpThreads) w2_s[i] = __ldg(p.w2t + i);
+    if (threadIdx.x < HP) b1_s[threadIdx.x] = __ldg(p.b1 + threadIdx.x);
+    if (threadIdx.x < CP) b2_s[threadIdx.x] = __ldg(p.b2 + threadIdx.x);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long G = gridDim.x;
+  const long long num_tiles = p.num_tiles;
+  const int KC = p.kc;
+
+  if (warp == kMlpConsumerWarps) {
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&xmap);
+      const uint64_t policy = make_evict_first_policy();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpConsumerWarps) {
+        const int nv = static_cast<int>(min(static_cast<long long>(kMlpConsumerWarps), (num_tiles - first + G - 1) / G));
+        for (int k = 0; k < KC; ++k) {
+          for (int w = 0; w < nv; ++w) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], kMlpStageBytes);
+            tma_load_2d(smem + static_cast<size_t>(stage) * kMlpStageBytes, &xmap, &full_bar[stage], k * kChunkF,
+                        static_cast<int>((first + w * G) * kMlpTileRows), policy);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const uint32_t lanebase = static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>(lane & 7) * 16u;
+    uint32_t seq_base = 0;
+    for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpConsumerWarps) {
+      const int nv = static_cast<int>(min(static_cast<long long>(kMlpConsumerWarps), (num_tiles - first + G - 1) / G));
+      if (warp < nv) {
+        const long long tile = first + warp * G;
+        float h[R][H];
+        float a1[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+#pragma unroll
+          for (int n = 0; n < H; ++n) h[j][n] = b1_s[n];
+          a1[j] = b1_s[H];
+        }
+        for (int k = 0; k < KC; ++k) {
+          const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + warp);
+          const uint32_t stage = seq % static_cast<uint32_t>(S);
+          const uint32_t phase = (seq / static_cast<uint32_t>(S)) & 1u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);  // previous occupant released (see linear_kernels.cu)
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t* xs = smem + static_cast<size_t>(stage) * kMlpStageBytes;
+          const float* wk = w1_s + k * kChunkF * HP;
+#pragma unroll 2
+          for (int q = 0; q < kChunkF / 4; ++q) {
+            float4 xv[R];
+            const uint32_t off = lanebase ^ static_cast<uint32_t>(q * 16);
+#pragma unroll
+            for (int j = 0; j < R; ++j) xv[j] = *reinterpret_cast<const float4*>(xs + off + j * 32 * 128);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float* wrow = wk + (q * 4 + e) * HP;
+              float x[R];
+#pragma unroll
+              for (int j = 0; j < R; ++j) x[j] = e == 0 ? xv[j].x : e == 1 ? xv[j].y : e == 2 ? xv[j].z : xv[j].w;
+#pragma unroll
+              for (int m = 0; m < H / 4; ++m) {
+                const float4 t = *reinterpret_cast<const float4*>(wrow + m * 4);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                  h[j][m * 4 + 0] = fmaf(x[j], t.x, h[j][m * 4 + 0]);
+                  h[j][m * 4 + 1] = fmaf(x[j], t.y, h[j][m * 4 + 1]);
+                  h[j][m * 4 + 2] = fmaf(x[j], t.z, h[j][m * 4 + 2]);
+                  h[j][m * 4 + 3] = fmaf(x[j], t.w, h[j][m * 4 + 3]);
+                }
+              }
+              if (EXACT) {
+                const float wmax = wrow[H];
+#pragma unroll
+                for (int j = 0; j < R; ++j) a1[j] = fmaf(fabsf(x[j]), wmax, a1[j]);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
+
+        // ---- ReLU, layer 2 (hidden unit outermost: each W2^T row is loaded once for the lane's 4 rows) ----
+        float z[R][NC2];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+          for (int c = 0; c < NC2; ++c) z[j][c] = b2_s[c];
+#pragma unroll
+        for (int n = 0; n < H; ++n) {
+          float w2v[NW2 * 4];
+#pragma unroll
+          for (int m = 0; m < NW2; ++m) {
+            const float4 t = *reinterpret_cast<const float4*>(w2_s + n * CP + m * 4);
+            w2v[m * 4 + 0] = t.x;
+            w2v[m * 4 + 1] = t.y;
+            w2v[m * 4 + 2] = t.z;
+            w2v[m * 4 + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const float hv = fmaxf(h[j][n], 0.f);
+#pragma unroll
+            for (int c = 0; c < NC2; ++c) z[j][c] = fmaf(hv, w2v[c], z[j][c]);
+          }
+        }
+        // ---- argmax (first maximum wins), margin guard, label store ----
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const long long row = tile * kMlpTileRows + lane + 32 * j;
+          float best = z[j][0];
+          float second = -INFINITY;
+          int idx = 0;
+#pragma unroll
+          for (int c = 1; c < C; ++c) {
+            if (z[j][c] > best) {
+              second = best;
+              best = z[j][c];
+              idx = c;
+            } else {
+              second = fmaxf(second, z[j][c]);
+            }
+          }
+          const bool in_range = row < p.n_rows;
+          if (in_range) p.labels[row] = idx;
+          if (EXACT) {
+            // |z_c - true| <= E1 * sum_n |w2_cn| + (H+4) u A2, E1 = (F+4) u A1 (ReLU is 1-Lipschitz)
+            const float err = p.e1_scale * a1[j] + p.e2_scale * z[j][C];
+            const bool certain = (best - second) > 2.0f * err;
+            const bool flagged = in_range && !certain;
+            const unsigned mask = __ballot_sync(0xffffffffu, flagged);
+            if (mask != 0u) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(p.flag_count, __popc(mask));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (flagged) {
+                const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
+              }
+            }
+          }
+        }
+      }
+      seq_base += static_cast<uint32_t>(KC * nv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp64 re-score / generic kernel: warp per row, lane per hidden unit
+// ---------------------------------------------------------------------------------------------------------------
+struct MlpRescoreParams {
+  const float* x;
+  long long ld;
+  long long n_rows;
+  const double* w1;  // [H][F]
+  const double* b1;
+  const double* w2;  // [C][H]
+  const double* b2;
+  int F, H, C;
+  const int* flag_count;
+  const int32_t* flag_rows;
+  int flag_cap;
+  int all_rows;
+  int32_t* labels;
+  unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
+  if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
+  const double u = 1.1102230246251565e-16;
+  for (long long i = warp_global; i < n; i += warps_total) {
+    const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
+    const float* xr = p.x + row * p.ld;
+    bool bad = false;
+    for (int f = lane; f < p.F; f += 32) bad |= !isfinite(xr[f]);
+    bad = __any_sync(0xffffffffu, bad);
+    // hidden units of this lane: n = lane, lane + 32, ... (H <= 256; the quickstart has 32: one per lane)
+    double hval[8], herr[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int hn = lane + 32 * t;
+      hval[t] = 0.0;
+      herr[t] = 0.0;
+      if (hn < p.H) {
+        const double* w1n = p.w1 + static_cast<long long>(hn) * p.F;
+        double hsum = p.b1[hn], habs = fabs(p.b1[hn]);
+        for (int f = 0; f < p.F; ++f) {
+          const double xv = static_cast<double>(xr[f]);
+          hsum = fma(xv, w1n[f], hsum);
+          habs = fma(fabs(xv), fabs(w1n[f]), habs);
+        }
+        hval[t] = fmax(hsum, 0.0);
+        herr[t] = (p.F + 2.0) * u * habs;  // the hidden unit's own fp64 rounding error
+      }
+    }
+    double best = 0.0, second = -INFINITY, amax = 0.0;
+    int idx = 0;
+    for (int c = 0; c < p.C; ++c) {
+      double s = 0.0, a = 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int hn = lane + 32 * t;
+        if (hn < p.H) {
+          const double w2 = p.w2[static_cast<long long>(c) * p.H + hn];
+          s = fma(hval[t], w2, s);
+          a += fabs(w2) * (hval[t] + herr[t]);
+        }
+      }
+      s = warp_sum(s) + p.b2[c];
+      a = warp_sum(a) + fabs(p.b2[c]);
+      amax = fmax(amax, a);
+      if (c == 0) {
+        best = s;
+      } else if (s > best) {
+        second = best;
+        best = s;
+        idx = c;
+      } else {
+        second = fmax(second, s);
+      }
+    }
+    if (lane == 0) {
+      p.labels[row] = idx;
+      if (bad) atomicAdd(&p.counters[1], 1ull);
+      const double err = (static_cast<double>(p.F + p.H) + 16.0) * u * amax;
+      if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static size_t mlp_fixed_smem(const MlpDeviceModel& m) {
+  return 1024 + (static_cast<size_t>(m.f_pad) * (m.n_hidden + 4) + (m.n_hidden + 4) + static_cast<size_t>(m.n_hidden) * m.cp + m.cp) * 4 +
+         2 * 64 * 8;
+}
+
+bool mlp_tma_supported(const MlpDeviceModel& m, std::string* why) {
+  const bool shape_ok = (m.n_hidden == 32 || m.n_hidden == 16) && (m.n_classes == 10 || m.n_classes == 2 || m.n_classes == 3);
+  if (!shape_ok) {
+    if (why) *why = "tile kernel instantiated for hidden in {16, 32} and classes in {2, 3, 10}";
+    return false;
+  }
+  if (mlp_fixed_smem(m) + kMlpConsumerWarps * static_cast<size_t>(kMlpStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
+    if (why) *why = "W1^T does not fit in shared memory next to a 4-stage ring";
+    return false;
+  }
+  return true;
+}
+
+template <int H, int C, bool EXACT>
+static cudaError_t mlp_launch_one(const CUtensorMap& xmap, const MlpKernelParams& p, int grid, size_t smem,
+                                  cudaStream_t stream) {
+  auto kern = mlp_argmax_tma_kernel<H, C, EXACT>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  kern<<<grid, kMlpThreads, smem, stream>>>(xmap, p);
+  return cudaGetLastError();
+}
+
+template <bool EXACT>
+static cudaError_t mlp_dispatch(int H, int C, const CUtensorMap& xmap, const MlpKernelParams& p, int grid, size_t smem,
+                                cudaStream_t stream) {
+#define UML_MLP_CASE(HH, CC) \
+  if (H == HH && C == CC) return mlp_launch_one<HH, CC, EXACT>(xmap, p, grid, smem, stream);
+  UML_MLP_CASE(32, 10) UML_MLP_CASE(32, 2) UML_MLP_CASE(32, 3) UML_MLP_CASE(16, 10) UML_MLP_CASE(16, 2) UML_MLP_CASE(16, 3)
+#undef UML_MLP_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, const float* x, int64_t n_rows,
+                           int32_t* labels, bool exact, const FlagList& flags, int sm_count, cudaStream_t stream) {
+  (void)x;
+  if (n_rows <= 0) return cudaSuccess;
+  MlpKernelParams p{};
+  p.w1t = m.w1t;
+  p.b1 = m.b1;
+  p.w2t = m.w2t;
+  p.b2 = m.b2;
+  p.labels = labels;
+  p.n_rows = n_rows;
+  p.num_tiles = (n_rows + kMlpTileRows - 1) / kMlpTileRows;
+  p.f_pad = m.f_pad;
+  p.kc = m.f_pad / kChunkF;
+  const size_t fixed = mlp_fixed_smem(m);
+  int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kMlpStageBytes);
+  stages = std::min(stages, 64);
+  if (const char* env = getenv("UML_B200_STAGES")) stages = std::max(kMlpConsumerWarps, std::min(stages, atoi(env)));
+  p.num_stages = stages;
+  const double u = 5.9604644775390625e-08;
+  const double F = m.n_in, H = m.n_hidden;
+  p.e1_scale = static_cast<float>((F + 4.0) * u * (1.0 + F * 4.76837158203125e-07) * 1.0001 * m.w2_abs_row_sum_max);
+  p.e2_scale = static_cast<float>((H + 4.0) * u * 1.0001);
+  p.flag_count = flags.count;
+  p.flag_rows = flags.rows;
+  p.flag_cap = flags.capacity;
+  const size_t smem = fixed + static_cast<size_t>(stages) * kMlpStageBytes;
+  const long long slots = (p.num_tiles + kMlpConsumerWarps - 1) / kMlpConsumerWarps;
+  const int grid = static_cast<int>(std::min<long long>(sm_count, std::max<long long>(1, slots)));
+  return exact ? mlp_dispatch<true>(m.n_hidden, m.n_classes, xmap, p, grid, smem, stream)
+               : mlp_dispatch<false>(m.n_hidden, m.n_classes, xmap, p, grid, smem, stream);
+}
+
+cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, int32_t* labels,
+                                   const FlagList& flags, bool all_rows, int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  MlpRescoreParams p{};
+  p.x = x;
+  p.ld = ld;
+  p.n_rows = n_rows;
+  p.w1 = m.w1_64;
+  p.b1 = m.b1_64;
+  p.w2 = m.w2_64;
+  p.b2 = m.b2_64;
+  p.F = m.n_in;
+  p.H = m.n_hidden;
+  p.C = m.n_classes;
+  p.flag_count = flags.count;
+  p.flag_rows = flags.rows;
+  p.flag_cap = flags.capacity;
+  p.all_rows = all_rows ? 1 : 0;
+  p.labels = labels;
+  p.counters = flags.counters;
+  long long blocks = static_cast<long long>(sm_count) * 8;
+  if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 7) / 8);
+  mlp_rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace uml

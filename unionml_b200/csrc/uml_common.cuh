@@ -64,6 +64,26 @@ bool linear_tma_supported(const LinearDeviceModel& m, std::string* why);
 cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,
                                int sm_count, cudaStream_t stream);
 
+// 2-layer MLP (mlp_kernels.cu)
+struct MlpDeviceModel {
+  const float* w1t;  // [f_pad][H + 4], column H = max_n |w1_nf|
+  const float* b1;   // [H + 4], entry H = max_n |b1_n|
+  const float* w2t;  // [H][cp], column C = max_c |w2_cn|
+  const float* b2;   // [cp], entry C = max_c |b2_c|
+  const double* w1_64;  // [H][F]
+  const double* b1_64;
+  const double* w2_64;  // [C][H]
+  const double* b2_64;
+  int n_in, n_hidden, n_classes;
+  int cp, f_pad;
+  double w2_abs_row_sum_max;  // max_c sum_n |w2_cn|
+};
+bool mlp_tma_supported(const MlpDeviceModel& m, std::string* why);
+cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, const float* x, int64_t n_rows,
+                           int32_t* labels, bool exact, const FlagList& flags, int sm_count, cudaStream_t stream);
+cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, int32_t* labels,
+                                   const FlagList& flags, bool all_rows, int sm_count, cudaStream_t stream);
+
 // staging kernels (stage_kernels.cu)
 struct StageResult {  // device-side counters
   unsigned long long nonfinite;

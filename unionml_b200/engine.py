@@ -104,6 +104,16 @@ class LinearModel:
         self.engine._check(st)
 
 
+class MlpModel:
+    """A 2-layer ``Linear -> ReLU -> Linear`` classifier resident on the device."""
+
+    def __init__(self, engine: "Engine", handle: int, n_in: int, n_hidden: int, n_out: int):
+        self.engine = engine
+        self._h = handle
+        self.n_features, self.n_hidden, self.n_classes = n_in, n_hidden, n_out
+        self._fin = weakref.finalize(self, N.lib().uml_mlp_free, handle)
+
+
 class Batch:
     """Feature rows resident in HBM as fp32 row-major (the staged form of ``Dataset.get_features`` output)."""
 
@@ -201,6 +211,39 @@ class Engine:
         )
         self._check(st)
         return LinearModel(self, h.value, n_features, max(n_classes, 2), None if classes is None else np.asarray(classes))
+
+    def load_mlp(self, w1, b1, w2, b2) -> MlpModel:
+        """``torch.nn.Linear`` layout: ``w1`` (hidden, in), ``b1`` (hidden), ``w2`` (out, hidden), ``b2`` (out); fp32."""
+        w1, b1, w2, b2 = (np.ascontiguousarray(a, dtype=np.float32) for a in (w1, b1, w2, b2))
+        n_hidden, n_in = w1.shape
+        n_out = w2.shape[0]
+        if b1.shape != (n_hidden,) or w2.shape != (n_out, n_hidden) or b2.shape != (n_out,):
+            raise ValueError(f"inconsistent MLP shapes {w1.shape} {b1.shape} {w2.shape} {b2.shape}")
+        h = C.c_void_p()
+        st = N.lib().uml_mlp_load(
+            self._h, C.byref(h), *(a.ctypes.data_as(C.c_void_p) for a in (w1, b1, w2, b2)), n_in, n_hidden, n_out
+        )
+        self._check(st)
+        return MlpModel(self, h.value, n_in, n_hidden, n_out)
+
+    def predict_mlp(self, model: MlpModel, batch: Batch, exact: bool = True, out_device_ptr: Optional[int] = None,
+                    want_stats: bool = True) -> Tuple[Optional[np.ndarray], Optional[dict]]:
+        """Argmax class index per row of ``softmax(W2 relu(W1 x + b1) + b2)``."""
+        mode = N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST
+        stats = N.Stats() if want_stats else None
+        with self._lock:
+            if out_device_ptr is not None:
+                st = N.lib().uml_mlp_predict(
+                    self._h, model._h, batch._h, C.c_void_p(out_device_ptr), 1, mode, C.byref(stats) if stats else None
+                )
+                self._check(st)
+                return None, stats.as_dict() if stats else None
+            out = np.empty(batch.n_rows, dtype=np.int32)
+            st = N.lib().uml_mlp_predict(
+                self._h, model._h, batch._h, out.ctypes.data_as(C.c_void_p), 0, mode, C.byref(stats) if stats else None
+            )
+        self._check(st)
+        return out, stats.as_dict() if stats else None
 
     def stage(self, features: Any, keep_f64: bool = True, check_finite: bool = True) -> Batch:
         """Host rows (ndarray / DataFrame, any order, f32/f64/int) -> device fp32 row-major, converted on the GPU."""

@@ -21,7 +21,7 @@ from typing import Any, List
 
 import numpy as np
 
-from unionml_b200.engine import Engine, LinearModel, get_engine
+from unionml_b200.engine import Engine, LinearModel, MlpModel, get_engine
 
 _cache_lock = threading.Lock()
 _model_cache: "weakref.WeakKeyDictionary[Any, tuple]" = weakref.WeakKeyDictionary()
@@ -94,3 +94,47 @@ def linear_predict_labels(estimator, features, exact: bool | None = None, engine
 def linear_argmax(estimator: Any, features: Any) -> List[float]:
     """Drop-in body for ``@model.predictor``: class labels as Python floats."""
     return linear_predict_labels(estimator, features).astype(np.float64).tolist()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PyTorch 2-layer MLP predictor (reference: tests/integration/pytorch_app/quickstart.py:14-24, 31-32, 68-70)
+# ---------------------------------------------------------------------------------------------------------------
+def _mlp_layers(module):
+    """The two ``nn.Linear`` layers of a ``Linear -> ReLU -> Linear`` module (any container layout)."""
+    import torch.nn as nn
+
+    leaves = [m for m in module.modules() if len(list(m.children())) == 0]
+    kinds = [type(m) for m in leaves]
+    if len(leaves) != 3 or kinds[0] is not nn.Linear or kinds[1] is not nn.ReLU or kinds[2] is not nn.Linear:
+        raise TypeError(
+            f"mlp_argmax supports Linear -> ReLU -> Linear modules (the reference's PytorchModel); found {kinds}"
+        )
+    return leaves[0], leaves[2]
+
+
+def device_mlp(module, engine: Engine | None = None) -> MlpModel:
+    engine = engine or get_engine()
+    l1, l2 = _mlp_layers(module)
+    w1, b1, w2, b2 = (t.detach().cpu().numpy() for t in (l1.weight, l1.bias, l2.weight, l2.bias))
+    key = (id(engine), w1.shape, w2.shape, hash(w1.tobytes()), hash(b1.tobytes()), hash(w2.tobytes()), hash(b2.tobytes()))
+    with _cache_lock:
+        hit = _model_cache.get(module)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dm = engine.load_mlp(w1, b1, w2, b2)
+        _model_cache[module] = (key, dm)
+        return dm
+
+
+def mlp_argmax(module: Any, features: Any) -> List[float]:
+    """Drop-in body for the torch quickstart predictor
+    ``[float(x) for x in module(process_features(features)).argmax(1)]``: features are cast to float32 exactly as
+    ``process_features`` does (``torch.from_numpy(features.values).float()``), the forward pass and argmax run on
+    the GPU, labels come back as Python floats."""
+    engine = get_engine()
+    dm = device_mlp(module, engine)
+    arr = features.to_numpy() if hasattr(features, "to_numpy") else np.asarray(features)
+    batch = engine.stage(arr, keep_f64=False)
+    idx, _ = engine.predict_mlp(dm, batch, exact=_exact_default())
+    batch.free()
+    return idx.astype(np.float64).tolist()
