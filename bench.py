@@ -289,7 +289,8 @@ def run_gpu_arm(args):
     gather = "none" if world == 1 else args.gather
     if world > 1 and gather == "fused":
         try:
-            exchange = PeerLabelExchange(rows * world, dev)
+            exchange = PeerLabelExchange(rows * world, dev, dtype=torch.uint8 if args.wire == "u8" else torch.int32,
+                                         multicast=not args.no_multicast)
         except Exception as exc:  # symmetric memory unavailable on this box: fall back to the NCCL all-gather
             if rank == 0:
                 print(f"bench: symmetric memory unavailable ({exc!r}); using nccl all-gather", file=sys.stderr)
@@ -316,7 +317,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    args.gather_used = {"fused": "fused peer stores from the kernel epilogue over NVLink (symmetric memory) + barrier",
+    how = "one NVLS multicast store per tile" if (exchange is not None and exchange.multicast) else "one store per peer per tile"
+    args.gather_used = {"fused": f"fused label stores ({args.wire}, {how}) from the kernel epilogue over NVLink (symmetric memory) + barrier",
                         "nccl": "ncclAllGather of int32 labels", "none": "none"}[gather]
     for _ in range(max(args.warmup, 3)):
         step()
@@ -344,12 +346,30 @@ def run_gpu_arm(args):
     # ---- roofline of the dominant kernel: CUDA events around linear_argmax_tma inside the library, live ----
     k_ms, r_ms, flagged, launches_per_step = [], [], 0, 2
     for _ in range(args.steps):
-        _, st = eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=True)
+        if exchange is not None:  # time the variant the step really runs: tile kernel with peer stores in its epilogue
+            st = eng.predict_peers(model, batch, exchange.peer_ptrs, rank * rows, exact=True, want_stats=True,
+                                   label_bytes=exchange.label_bytes)
+            exchange.barrier()
+        else:
+            _, st = eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=True)
         k_ms.append(st["kernel_ms"])
         r_ms.append(st["recheck_ms"])
         flagged = st["n_flagged"]
         launches_per_step = st["kernel_launches"]
     kernel_ms = statistics.mean(k_ms)
+    exchange_ms = None
+    if world > 1:  # cost of the label exchange alone (barrier or all-gather), CUDA events, same stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            if exchange is not None:
+                exchange.barrier()
+            else:
+                dist.all_gather_into_tensor(labels_all, labels_local)
+        e1.record(stream)
+        barrier()
+        exchange_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = measured_peak_hbm()
     achieved = rows * BYTES_PER_ROW / (kernel_ms * 1e-3) / 1e9
@@ -365,6 +385,7 @@ def run_gpu_arm(args):
         "kernel_ms": kernel_ms,
         "kernel_ms_min": min(k_ms),
         "rescore_ms": statistics.mean(r_ms),
+        "exchange_ms": exchange_ms,
         "algorithmic_bytes_per_launch": rows * BYTES_PER_ROW,
         "rows_rescored_fp64": flagged,
     }
@@ -382,7 +403,9 @@ def run_gpu_arm(args):
             e2e_t.append(dt)
     if args.skip_e2e:  # profiling runs only (ncu): the JSON line of such a run is never a bench value
         eng.predict_host(model, X_host[:1_000_000], exact=True, out=labels_host[:1_000_000])
-        labels_host[:] = labels_local.cpu().numpy()
+        tmp_i32 = torch.empty(rows, dtype=torch.int32, device=dev)
+        eng.predict(model, batch, exact=True, out_device_ptr=tmp_i32.data_ptr(), want_stats=False)
+        labels_host[:] = tmp_i32.cpu().numpy()
         e2e_t, e2e_stats = [float("nan")], {"h2d_bytes": 0, "d2h_bytes": 0, "total_ms": float("nan")}
     e2e_s = statistics.mean(e2e_t)
     if world > 1:
@@ -399,16 +422,18 @@ def run_gpu_arm(args):
         "steps": args.e2e_steps,
         "path": "Engine.predict_host: pinned fp32 rows -> chunked H2D -> linear_argmax_tma (+fp64 re-score) -> D2H int32 labels",
     }
+    local_i32 = torch.empty(rows, dtype=torch.int32, device=dev)
+    eng.predict(model, batch, exact=True, out_device_ptr=local_i32.data_ptr(), want_stats=False)
     if world > 1:
         # every rank must hold every rank's labels: compare the exchanged vector with a plain NCCL all-gather
         step()
         ref_all = torch.empty(rows * world, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(ref_all, labels_local.clone())
+        dist.all_gather_into_tensor(ref_all, local_i32)
         torch.cuda.synchronize()
-        if not torch.equal(ref_all, labels_all):
+        if not torch.equal(ref_all, labels_all.to(torch.int32)):
             raise SystemExit(f"bench: rank {rank}: exchanged label vector differs from the NCCL all-gather")
     # sanity: resident and streamed paths agree
-    check = labels_local.cpu().numpy()
+    check = local_i32.cpu().numpy()
     if not np.array_equal(check, labels_host):
         raise SystemExit("bench: resident and host-streamed label vectors differ")
 
@@ -472,6 +497,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: skip the host-buffer leg")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="label exchange for --gpus > 1")
+    ap.add_argument("--no-multicast", action="store_true", help="fused exchange: per-peer stores instead of NVLS multicast")
+    ap.add_argument("--wire", default="u8", choices=["u8", "i32"], help="label width of the fused exchange")
     ap.add_argument("--interleave", action="store_true", help="robustness check: run a cuBLAS GEMM between steps")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from the committed ncu capture")
     args = ap.parse_args()

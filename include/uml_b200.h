@@ -128,11 +128,12 @@ UML_API void uml_batch_free(uml_batch* b);
 UML_API int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
                        int labels_on_device, int mode, uml_stats* stats);
 /* fused compute + collective: every rank's kernel epilogue stores its labels straight into all peers' label vectors
- * over NVLink (peer_labels[0] = base of THIS rank's full-length int32 vector, peer_labels[1..] = the other ranks'
- * vectors, already mapped for peer access; this rank's rows land at row_offset in each).  Replaces kernel +
- * ncclAllGather; the caller still needs one cross-rank barrier before reading peers' rows. */
-UML_API int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* const* peer_labels,
-                             int n_peers, int64_t row_offset, int mode, uml_stats* stats);
+ * over NVLink (peer_labels[0] = base of THIS rank's full-length vector, peer_labels[1..] = the other ranks' vectors,
+ * already mapped for peer access; this rank's rows land at row_offset in each).  label_bytes = 4: int32 vectors;
+ * label_bytes = 1 (n_classes <= 256): uint8 vectors - a 128-row tile leaves as one 128-byte store per peer.
+ * Replaces kernel + ncclAllGather; the caller still needs one cross-rank barrier before reading peers' rows. */
+UML_API int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, void* const* peer_labels,
+                             int n_peers, int64_t row_offset, int label_bytes, int mode, uml_stats* stats);
 /* end to end from HOST rows to HOST labels in one call (the /predict and Model.predict(features=...) shape): chunked
  * H2D, staging kernel, scoring kernel and label D2H pipelined on two streams; never holds more than a few chunks in
  * HBM.  host_ptr/labels_out may be pageable or pinned (uml_host_alloc). */

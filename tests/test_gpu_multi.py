@@ -30,11 +30,12 @@ lo, hi = shard_bounds(N, rank, world); counts = shard_counts(N, world)
 b = eng.stage(X[lo:hi])
 got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True)            # NCCL all-gather
 torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy(), want), "nccl path"
-ex = PeerLabelExchange(N, dev)
-for _ in range(3):
-    ex.labels.fill_(-1); ex.barrier()
-    got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True, exchange=ex)  # fused peer stores
-    torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy(), want), "fused path"
+for dtype, mc in ((torch.int32, False), (torch.uint8, False), (torch.uint8, True), (torch.int32, True)):
+    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc)   # fused stores: per-peer or NVLS multicast
+    for _ in range(3):
+        ex.labels.fill_(99); ex.barrier()
+        got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True, exchange=ex)
+        torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy().astype(np.int32), want), f"fused path {dtype}"
 dist.barrier(); dist.destroy_process_group()
 print(f"rank {rank} ok")
 '''

@@ -653,12 +653,15 @@ static int finish_stats(uml_engine* e, uml_stats* stats, int64_t n_rows, int lau
 }
 
 static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
-                          int labels_on_device, int32_t* const* peers, int n_peers, int64_t row_offset, int mode,
-                          uml_stats* stats) {
+                          int labels_on_device, void* const* peers, int n_peers, int64_t row_offset, int label_bytes,
+                          int mode, uml_stats* stats) {
   if (!e || !m || !b) return UML_ERR_INVALID;
   if (!labels_out && b->n_rows > 0 && n_peers == 0) return UML_ERR_INVALID;
   if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
   if (n_peers < 0 || n_peers > 8) UML_FAIL(e, UML_ERR_INVALID, "n_peers %d (max 8)", n_peers);
+  if (n_peers > 0 && label_bytes != 1 && label_bytes != 4) UML_FAIL(e, UML_ERR_INVALID, "label_bytes %d", label_bytes);
+  if (n_peers > 0 && label_bytes == 1 && m->dm.n_classes > 256)
+    UML_FAIL(e, UML_ERR_UNSUPPORTED, "byte labels need n_classes <= 256 (model has %d)", m->dm.n_classes);
   if (b->n_features != m->n_features_in)
     UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.",
              b->n_features, m->n_features_in);
@@ -671,11 +674,14 @@ static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b,
   int rc;
   if (exact && (rc = ensure_flags(e, b->n_rows)) != UML_OK) return rc;
   int32_t* d_labels = labels_out;
-  if (!labels_out && n_peers > 0) {
+  const bool wire_u8 = n_peers > 0 && label_bytes == 1;
+  if (!labels_out && n_peers > 0 && !wire_u8) {
     // fused exchange: entry 0 is this rank's own full-length vector -> it is the local label target
-    d_labels = peers[0] + row_offset;
+    d_labels = static_cast<int32_t*>(peers[0]) + row_offset;
     peers += 1;
     n_peers -= 1;
+  } else if (!labels_out && wire_u8) {
+    d_labels = nullptr;  // byte vectors everywhere (own vector included among the peers); no int32 copy kept
   } else if (!labels_on_device || !labels_out) {
     if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
     d_labels = e->d_labels;
@@ -691,6 +697,7 @@ static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b,
   l.n_rows = b->n_rows;
   l.labels = d_labels;
   l.n_peers = n_peers;
+  l.wire_u8 = wire_u8 ? 1 : 0;
   for (int i = 0; i < n_peers; ++i) l.peers[i] = peers[i];
   l.row_offset = row_offset;
   int launches = 0, path = 0;
@@ -713,14 +720,14 @@ static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b,
 
 int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* labels_out,
                        int labels_on_device, int mode, uml_stats* stats) {
-  return predict_common(e, m, b, labels_out, labels_on_device, nullptr, 0, 0, mode, stats);
+  return predict_common(e, m, b, labels_out, labels_on_device, nullptr, 0, 0, 4, mode, stats);
 }
 
-int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, int32_t* const* peer_labels,
-                             int n_peers, int64_t row_offset, int mode, uml_stats* stats) {
+int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, void* const* peer_labels,
+                             int n_peers, int64_t row_offset, int label_bytes, int mode, uml_stats* stats) {
   if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
   // peer_labels[0] must be this rank's own vector (local target); labels land at peer_labels[i] + row_offset for all i
-  return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, mode, stats);
+  return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, label_bytes, mode, stats);
 }
 
 int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,

@@ -28,8 +28,9 @@ struct TmaKernelParams {
   const float* wt;    // [f_pad][CP]
   const float* bias;  // [CP]
   int32_t* labels;
-  int32_t* peers[8];
+  void* peers[8];
   int n_peers;
+  int wire_u8;  // peer vectors hold one byte per label (classes <= 256) instead of int32
   long long row_offset;
   long long n_rows;
   long long num_tiles;
@@ -172,6 +173,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
         }
 
         // ---- fused epilogue: argmax (first maximum wins), margin guard, label store (+ peer stores) ----
+        int idxs[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const long long row = tile * kTileRows + lane + 32 * j;
@@ -189,10 +191,12 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
               second = fmaxf(second, v);
             }
           }
+          idxs[j] = idx;
           const bool in_range = row < p.n_rows;
           if (in_range) {
-            p.labels[row] = idx;
-            for (int i = 0; i < p.n_peers; ++i) p.peers[i][p.row_offset + row] = idx;
+            if (p.labels) p.labels[row] = idx;
+            if (!p.wire_u8)
+              for (int i = 0; i < p.n_peers; ++i) static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idx;
           }
           if (EXACT) {
             // certain iff margin > 2 * err, err <= (F+4) 2^-24 A; NaN/Inf anywhere makes the comparison false
@@ -208,6 +212,29 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
                 if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
               }
             }
+          }
+        }
+        if (p.wire_u8 && p.n_peers > 0) {
+          // byte labels on the wire: transpose through shuffles so lane l holds rows 4l..4l+3 of the tile and the
+          // whole 128-row tile leaves as ONE coalesced 128-byte store per peer (instead of four int32 stores)
+          const uint32_t packed = static_cast<uint32_t>(idxs[0]) | (static_cast<uint32_t>(idxs[1]) << 8) |
+                                  (static_cast<uint32_t>(idxs[2]) << 16) | (static_cast<uint32_t>(idxs[3]) << 24);
+          uint32_t word = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t w = __shfl_sync(0xffffffffu, packed, (4 * lane + t) & 31);
+            word |= ((w >> (8 * (lane >> 3))) & 0xffu) << (8 * t);
+          }
+          const long long row4 = tile * kTileRows + 4 * lane;
+          const long long at = p.row_offset + row4;
+          if (row4 + 3 < p.n_rows && (at & 3) == 0) {
+            for (int i = 0; i < p.n_peers; ++i)
+              *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.peers[i]) + at) = word;
+          } else {
+            for (int t = 0; t < 4; ++t)
+              if (row4 + t < p.n_rows)
+                for (int i = 0; i < p.n_peers; ++i)
+                  static_cast<uint8_t*>(p.peers[i])[at + t] = static_cast<uint8_t>((word >> (8 * t)) & 0xffu);
           }
         }
       }
@@ -232,8 +259,9 @@ struct RescoreParams {
   int flag_cap;
   int all_rows;
   int32_t* labels;
-  int32_t* peers[8];
+  void* peers[8];
   int n_peers;
+  int wire_u8;
   long long row_offset;
   unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] flagged (re-scored) rows
 };
@@ -280,8 +308,11 @@ __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p)
     }
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
-      p.labels[row] = idx;
-      for (int q = 0; q < p.n_peers; ++q) p.peers[q][p.row_offset + row] = idx;
+      if (p.labels) p.labels[row] = idx;
+      for (int q = 0; q < p.n_peers; ++q) {
+        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(idx);
+        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
+      }
       if (bad) atomicAdd(&p.counters[1], 1ull);
       // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
       const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
@@ -345,6 +376,7 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
   p.bias = m.bias;
   p.labels = l.labels;
   p.n_peers = l.n_peers;
+  p.wire_u8 = l.wire_u8;
   for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
   p.row_offset = l.row_offset;
   p.n_rows = l.n_rows;
@@ -389,6 +421,7 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   p.all_rows = all_rows ? 1 : 0;
   p.labels = l.labels;
   p.n_peers = l.n_peers;
+  p.wire_u8 = l.wire_u8;
   for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
   p.row_offset = l.row_offset;
   p.counters = flags.counters;

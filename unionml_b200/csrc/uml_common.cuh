@@ -52,8 +52,9 @@ struct LinearLaunch {
   int64_t n_rows;
   int32_t* labels;      // local label vector (device)
   // fused all-gather epilogue: labels are also stored to peers[i] + row_offset for i < n_peers
-  int32_t* peers[8];
+  void* peers[8];
   int n_peers;
+  int wire_u8;  // 1: peer vectors are uint8 (one byte per label), 0: int32
   int64_t row_offset;
 };
 

@@ -301,14 +301,14 @@ class Engine:
         return out, stats.as_dict() if stats else None
 
     def predict_peers(self, model: LinearModel, batch: Batch, peer_ptrs, row_offset: int, exact: bool = True,
-                      want_stats: bool = False) -> Optional[dict]:
+                      want_stats: bool = False, label_bytes: int = 4) -> Optional[dict]:
         """Fused compute + all-gather: labels are stored into every peer's vector from the kernel epilogue."""
         mode = N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST
         arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
         stats = N.Stats() if want_stats else None
         with self._lock:
             st = N.lib().uml_linear_predict_peers(
-                self._h, model._h, batch._h, arr, len(peer_ptrs), row_offset, mode, C.byref(stats) if stats else None
+                self._h, model._h, batch._h, arr, len(peer_ptrs), row_offset, label_bytes, mode, C.byref(stats) if stats else None
             )
         self._check(st)
         return stats.as_dict() if stats else None

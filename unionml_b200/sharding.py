@@ -50,19 +50,30 @@ def gather_labels(local: torch.Tensor, counts: Sequence[int], group=None) -> tor
 
 
 class PeerLabelExchange:
-    """A full-length int32 label vector in symmetric memory on every rank + the peers' device pointers."""
+    """A full-length label vector (int32, or uint8 on the wire) in symmetric memory on every rank + peer pointers."""
 
-    def __init__(self, total_rows: int, device: torch.device, group=None):
+    def __init__(self, total_rows: int, device: torch.device, group=None, dtype: torch.dtype = torch.int32,
+                 multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
+        if dtype not in (torch.int32, torch.uint8):
+            raise ValueError("label vectors are int32 or uint8 (byte labels need n_classes <= 256)")
         self.group = group if group is not None else dist.group.WORLD
-        self.labels = symm_mem.empty(total_rows, dtype=torch.int32, device=device)
+        self.label_bytes = 1 if dtype == torch.uint8 else 4
+        self.labels = symm_mem.empty(total_rows, dtype=dtype, device=device)
         self.handle = symm_mem.rendezvous(self.labels, self.group)
         self.rank = self.handle.rank
         self.world = self.handle.world_size
         ptrs = list(self.handle.buffer_ptrs)
-        # own pointer first: the kernel treats entry 0 as its local label vector
-        self.peer_ptrs = [ptrs[self.rank]] + [p for r, p in enumerate(ptrs) if r != self.rank]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
+        self.multicast = mc != 0
+        if self.multicast:
+            # NVLS: one store to the multicast address is replicated by the switch into every rank's vector (own
+            # included), so the kernel issues a single store per tile however many GPUs take part
+            self.peer_ptrs = [mc]
+        else:
+            # own pointer first: the kernel treats entry 0 as its local label vector
+            self.peer_ptrs = [ptrs[self.rank]] + [p for r, p in enumerate(ptrs) if r != self.rank]
 
     def barrier(self) -> None:
         """All ranks' stores have landed everywhere (device-side barrier on the current stream)."""
@@ -75,7 +86,7 @@ def predict_sharded(engine, model, batch, *, row_offset: int, counts: Sequence[i
     """Score this rank's resident shard and return the full label vector (device tensor, identical on all ranks)."""
     rank = dist.get_rank(group)
     if exchange is not None:
-        engine.predict_peers(model, batch, exchange.peer_ptrs, row_offset, exact=exact)
+        engine.predict_peers(model, batch, exchange.peer_ptrs, row_offset, exact=exact, label_bytes=exchange.label_bytes)
         exchange.barrier()
         return exchange.labels
     if labels_all is None:
