@@ -4,7 +4,7 @@
 // (/root/reference/tests/integration/pytorch_app/quickstart.py:14-24, 68-70; hyperparameters 64 -> 32 -> 10 at :80).
 //
 //  * mlp_argmax_tma_kernel<H, C, EXACT>: the same persistent TMA + mbarrier ring (128-row x 32-feature boxes) as the
-//    linear kernel, but 4 consumer warps per CTA so a lane can carry H hidden accumulators for each of its 4 rows.  Layer 1 runs per
+//    linear kernel; consumer warps work in pairs on a box (64 rows each, 2 rows x H hidden accumulators per lane).  Layer 1 runs per
 //    landed box (W1^T rows are warp-uniform broadcast LDS.128 from shared memory), then ReLU, layer 2 and the argmax are
 //    fused in registers.  EXACT mode carries two bound accumulators (A1 over layer 1, A2 over layer 2) and re-scores
 //    rows whose logit margin is inside the propagated fp32 error bound in fp64.
@@ -21,13 +21,15 @@
 
 namespace uml {
 
-// 4 consumer warps (one per SM sub-partition) + 1 producer warp = 160 threads: with 5 warps per CTA a thread may hold up
-// to 255 registers, which is what 4 rows x 32 hidden accumulators per lane need (9 warps would cap it at 168).
-constexpr int kMlpConsumerWarps = 4;
+// 8 consumer warps work as 4 PAIRS: a pair shares one 128-row x 32-feature box, warp 2p takes rows 0..63 and warp 2p+1
+// rows 64..127 (2 rows per lane x 32 hidden accumulators = 64 registers, inside the 168-register cap of a 9-warp CTA)
+// and two warps per SM sub-partition hide each other's LDS / barrier latency.  A stage is released by both warps.
+constexpr int kMlpPairs = 4;
+constexpr int kMlpConsumerWarps = 2 * kMlpPairs;
 constexpr int kMlpThreads = (kMlpConsumerWarps + 1) * 32;
 constexpr int kMlpTileRows = kTileRows;                      // 128 rows x 32 features, same boxes as the linear kernel
 constexpr int kMlpStageBytes = kStageBytes;                  // 16 KiB
-constexpr int kMlpRowsPerLane = kMlpTileRows / 32;           // 4
+constexpr int kMlpRowsPerLane = 2;                           // rows per lane within a warp's 64-row half
 
 struct MlpKernelParams {
   const float* w1t;  // [f_pad][H + 4]   column H = max_n |w1_nf|
@@ -79,7 +81,7 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // both warps of the pair that read the stage
     }
     fence_barrier_init();
   }
@@ -95,8 +97,8 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
       const uint64_t policy = make_evict_first_policy();
       int stage = 0;
       uint32_t phase = 0;
-      for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpConsumerWarps) {
-        const int nv = static_cast<int>(min(static_cast<long long>(kMlpConsumerWarps), (num_tiles - first + G - 1) / G));
+      for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpPairs) {
+        const int nv = static_cast<int>(min(static_cast<long long>(kMlpPairs), (num_tiles - first + G - 1) / G));
         for (int k = 0; k < KC; ++k) {
           for (int w = 0; w < nv; ++w) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -112,22 +114,24 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
       }
     }
   } else {
-    const uint32_t lanebase = static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>(lane & 7) * 16u;
+    const int pair = warp >> 1;
+    const int half = warp & 1;
+    const uint32_t lanebase = static_cast<uint32_t>(half * 64 + lane) * 128u + static_cast<uint32_t>(lane & 7) * 16u;
     uint32_t seq_base = 0;
-    for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpConsumerWarps) {
-      const int nv = static_cast<int>(min(static_cast<long long>(kMlpConsumerWarps), (num_tiles - first + G - 1) / G));
-      if (warp < nv) {
-        const long long tile = first + warp * G;
-        float h[R][H];
+    for (long long first = blockIdx.x; first < num_tiles; first += G * kMlpPairs) {
+      const int nv = static_cast<int>(min(static_cast<long long>(kMlpPairs), (num_tiles - first + G - 1) / G));
+      if (pair < nv) {
+        const long long tile = first + pair * G;
+        uint64_t h2[R][H / 2];  // hidden accumulators as fp32x2 pairs (units 2i, 2i+1)
         float a1[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
 #pragma unroll
-          for (int n = 0; n < H; ++n) h[j][n] = b1_s[n];
+          for (int n = 0; n < H / 2; ++n) h2[j][n] = pack2(b1_s[2 * n], b1_s[2 * n + 1]);
           a1[j] = b1_s[H];
         }
         for (int k = 0; k < KC; ++k) {
-          const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + warp);
+          const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + pair);
           const uint32_t stage = seq % static_cast<uint32_t>(S);
           const uint32_t phase = (seq / static_cast<uint32_t>(S)) & 1u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);  // previous occupant released (see linear_kernels.cu)
@@ -149,12 +153,12 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
 #pragma unroll
               for (int m = 0; m < H / 4; ++m) {
                 const float4 t = *reinterpret_cast<const float4*>(wrow + m * 4);
+                const uint64_t w01 = pack2(t.x, t.y), w23 = pack2(t.z, t.w);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                  h[j][m * 4 + 0] = fmaf(x[j], t.x, h[j][m * 4 + 0]);
-                  h[j][m * 4 + 1] = fmaf(x[j], t.y, h[j][m * 4 + 1]);
-                  h[j][m * 4 + 2] = fmaf(x[j], t.z, h[j][m * 4 + 2]);
-                  h[j][m * 4 + 3] = fmaf(x[j], t.w, h[j][m * 4 + 3]);
+                  const uint64_t xx = pack2(x[j], x[j]);
+                  h2[j][m * 2 + 0] = fma2(xx, w01, h2[j][m * 2 + 0]);
+                  h2[j][m * 2 + 1] = fma2(xx, w23, h2[j][m * 2 + 1]);
                 }
               }
               if (EXACT) {
@@ -169,33 +173,48 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
         }
 
         // ---- ReLU, layer 2 (hidden unit outermost: each W2^T row is loaded once for the lane's 4 rows) ----
-        float z[R][NC2];
+        constexpr int NZ2 = (NC2 + 1) / 2;  // logit accumulators as pairs (a padding lane multiplies a zero weight)
+        uint64_t z2[R][NZ2];
 #pragma unroll
         for (int j = 0; j < R; ++j)
 #pragma unroll
-          for (int c = 0; c < NC2; ++c) z[j][c] = b2_s[c];
+          for (int c = 0; c < NZ2; ++c) z2[j][c] = pack2(b2_s[2 * c], 2 * c + 1 < CP ? b2_s[2 * c + 1] : 0.f);
 #pragma unroll
-        for (int n = 0; n < H; ++n) {
-          float w2v[NW2 * 4];
-#pragma unroll
-          for (int m = 0; m < NW2; ++m) {
-            const float4 t = *reinterpret_cast<const float4*>(w2_s + n * CP + m * 4);
-            w2v[m * 4 + 0] = t.x;
-            w2v[m * 4 + 1] = t.y;
-            w2v[m * 4 + 2] = t.z;
-            w2v[m * 4 + 3] = t.w;
-          }
+        for (int n2 = 0; n2 < H / 2; ++n2) {
+          float hv[R][2];
 #pragma unroll
           for (int j = 0; j < R; ++j) {
-            const float hv = fmaxf(h[j][n], 0.f);
+            unpack2(h2[j][n2], hv[j][0], hv[j][1]);
+            hv[j][0] = fmaxf(hv[j][0], 0.f);
+            hv[j][1] = fmaxf(hv[j][1], 0.f);
+          }
 #pragma unroll
-            for (int c = 0; c < NC2; ++c) z[j][c] = fmaf(hv, w2v[c], z[j][c]);
+          for (int u = 0; u < 2; ++u) {
+            const int n = 2 * n2 + u;
+            uint64_t w2p[NW2 * 2];
+#pragma unroll
+            for (int m = 0; m < NW2; ++m) {
+              const float4 t = *reinterpret_cast<const float4*>(w2_s + n * CP + m * 4);
+              w2p[m * 2 + 0] = pack2(t.x, t.y);
+              w2p[m * 2 + 1] = pack2(t.z, t.w);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const uint64_t hh = pack2(hv[j][u], hv[j][u]);
+#pragma unroll
+              for (int c = 0; c < NZ2; ++c) z2[j][c] = fma2(hh, w2p[c], z2[j][c]);
+            }
           }
         }
+        float z[R][2 * NZ2];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+          for (int c = 0; c < NZ2; ++c) unpack2(z2[j][c], z[j][2 * c], z[j][2 * c + 1]);
         // ---- argmax (first maximum wins), margin guard, label store ----
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          const long long row = tile * kMlpTileRows + lane + 32 * j;
+          const long long row = tile * kMlpTileRows + half * 64 + lane + 32 * j;
           float best = z[j][0];
           float second = -INFINITY;
           int idx = 0;
@@ -335,7 +354,7 @@ bool mlp_tma_supported(const MlpDeviceModel& m, std::string* why) {
     if (why) *why = "tile kernel instantiated for hidden in {16, 32} and classes in {2, 3, 10}";
     return false;
   }
-  if (mlp_fixed_smem(m) + kMlpConsumerWarps * static_cast<size_t>(kMlpStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
+  if (mlp_fixed_smem(m) + kMlpPairs * static_cast<size_t>(kMlpStageBytes) > static_cast<size_t>(kMaxSmemBytes)) {
     if (why) *why = "W1^T does not fit in shared memory next to a 4-stage ring";
     return false;
   }
@@ -379,7 +398,7 @@ cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, con
   const size_t fixed = mlp_fixed_smem(m);
   int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kMlpStageBytes);
   stages = std::min(stages, 64);
-  if (const char* env = getenv("UML_B200_STAGES")) stages = std::max(kMlpConsumerWarps, std::min(stages, atoi(env)));
+  if (const char* env = getenv("UML_B200_STAGES")) stages = std::max(kMlpPairs, std::min(stages, atoi(env)));
   p.num_stages = stages;
   const double u = 5.9604644775390625e-08;
   const double F = m.n_in, H = m.n_hidden;
@@ -389,7 +408,7 @@ cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, con
   p.flag_rows = flags.rows;
   p.flag_cap = flags.capacity;
   const size_t smem = fixed + static_cast<size_t>(stages) * kMlpStageBytes;
-  const long long slots = (p.num_tiles + kMlpConsumerWarps - 1) / kMlpConsumerWarps;
+  const long long slots = (p.num_tiles + kMlpPairs - 1) / kMlpPairs;
   const int grid = static_cast<int>(std::min<long long>(sm_count, std::max<long long>(1, slots)));
   return exact ? mlp_dispatch<true>(m.n_hidden, m.n_classes, xmap, p, grid, smem, stream)
                : mlp_dispatch<false>(m.n_hidden, m.n_classes, xmap, p, grid, smem, stream);
