@@ -236,6 +236,7 @@ def workload_config(args, n_gpus: int) -> dict:
         "n_features": N_FEATURES,
         "n_classes": 10,
         "mode": "exact (fp32 tile kernel + margin guard + fp64 re-score; labels == sklearn float64 labels)",
+        "labels": f"{args.wire} class index per row",
         "parallelism": (f"row-sharded x{n_gpus}, label exchange: " + getattr(args, "gather_used", args.gather))
         if n_gpus > 1
         else "single GPU",
@@ -287,30 +288,39 @@ def run_gpu_arm(args):
     counts = [rows] * world
     exchange = None
     gather = "none" if world == 1 else args.gather
-    if world > 1 and gather == "fused":
+    if world > 1 and gather in ("fused", "push"):
         try:
             exchange = PeerLabelExchange(rows * world, dev, dtype=torch.uint8 if args.wire == "u8" else torch.int32,
-                                         multicast=not args.no_multicast)
+                                         multicast=not args.no_multicast, push=args.gather == "push")
         except Exception as exc:  # symmetric memory unavailable on this box: fall back to the NCCL all-gather
             if rank == 0:
                 print(f"bench: symmetric memory unavailable ({exc!r}); using nccl all-gather", file=sys.stderr)
             gather = "nccl"
-    labels_all = exchange.labels if exchange is not None else torch.empty(rows * world, dtype=torch.int32, device=dev)
+    # label vectors are uint8 class indices (n_classes = 10 <= 256): 4x fewer bytes to write and to exchange
+    wire_dtype = torch.uint8 if args.wire == "u8" else torch.int32
+    label_bytes = 1 if args.wire == "u8" else 4
+    labels_all = exchange.labels if exchange is not None else torch.empty(rows * world, dtype=wire_dtype, device=dev)
     labels_local = labels_all[rank * rows : (rank + 1) * rows]
-
     interleave = interleave_out = None
     if args.interleave:
         interleave = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
         interleave_out = torch.empty_like(interleave)
 
+    def local_predict(want_stats=False):
+        """Score the resident shard into this rank's slice of the label vector (no exchange)."""
+        return eng.predict_peers(model, batch, [labels_all.data_ptr()], rank * rows, exact=True, want_stats=want_stats,
+                                 label_bytes=label_bytes)
+
     def step():
         if world == 1:
-            eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=False)
+            local_predict()
             if interleave is not None:  # --interleave: a foreign kernel between steps (robustness check, not a bench)
                 torch.matmul(interleave, interleave, out=interleave_out)
-        else:
-            predict_sharded(eng, model, batch, row_offset=rank * rows, counts=counts, exact=True, exchange=exchange,
-                            labels_all=labels_all)
+        elif exchange is not None:
+            predict_sharded(eng, model, batch, row_offset=rank * rows, counts=counts, exact=True, exchange=exchange)
+        else:  # nccl
+            local_predict()
+            dist.all_gather_into_tensor(labels_all, labels_local)
 
     def barrier():
         if world > 1:
@@ -318,7 +328,8 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     how = "one NVLS multicast store per tile" if (exchange is not None and exchange.multicast) else "one store per peer per tile"
-    args.gather_used = {"fused": f"fused label stores ({args.wire}, {how}) from the kernel epilogue over NVLink (symmetric memory) + barrier",
+    args.gather_used = {"push": f"kernel stores {args.wire} labels locally, thin copy kernel pushes the slice ({how.replace(' per tile', '')}) + barrier",
+                        "fused": f"fused label stores ({args.wire}, {how}) from the kernel epilogue over NVLink (symmetric memory) + barrier",
                         "nccl": "ncclAllGather of int32 labels", "none": "none"}[gather]
     for _ in range(max(args.warmup, 3)):
         step()
@@ -346,12 +357,12 @@ def run_gpu_arm(args):
     # ---- roofline of the dominant kernel: CUDA events around linear_argmax_tma inside the library, live ----
     k_ms, r_ms, flagged, launches_per_step = [], [], 0, 2
     for _ in range(args.steps):
-        if exchange is not None:  # time the variant the step really runs: tile kernel with peer stores in its epilogue
+        if exchange is not None and not exchange.push:  # the variant the step really runs: stores to all ranks in the epilogue
             st = eng.predict_peers(model, batch, exchange.peer_ptrs, rank * rows, exact=True, want_stats=True,
                                    label_bytes=exchange.label_bytes)
             exchange.barrier()
         else:
-            _, st = eng.predict(model, batch, exact=True, out_device_ptr=labels_local.data_ptr(), want_stats=True)
+            st = local_predict(want_stats=True)
         k_ms.append(st["kernel_ms"])
         r_ms.append(st["recheck_ms"])
         flagged = st["n_flagged"]
@@ -364,6 +375,10 @@ def run_gpu_arm(args):
         e0.record(stream)
         for _ in range(args.steps):
             if exchange is not None:
+                if exchange.push:
+                    off = rank * rows * exchange.label_bytes
+                    remote = exchange.peer_ptrs if exchange.multicast else exchange.peer_ptrs[1:]
+                    eng.push_labels(exchange.own_ptr + off, [p + off for p in remote], rows * exchange.label_bytes)
                 exchange.barrier()
             else:
                 dist.all_gather_into_tensor(labels_all, labels_local)
@@ -424,6 +439,11 @@ def run_gpu_arm(args):
     }
     local_i32 = torch.empty(rows, dtype=torch.int32, device=dev)
     eng.predict(model, batch, exact=True, out_device_ptr=local_i32.data_ptr(), want_stats=False)
+    if world == 1:
+        step()
+        torch.cuda.synchronize()
+        if not torch.equal(labels_local.to(torch.int32), local_i32):
+            raise SystemExit("bench: uint8 label vector differs from the int32 one")
     if world > 1:
         # every rank must hold every rank's labels: compare the exchanged vector with a plain NCCL all-gather
         step()
@@ -496,7 +516,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="bounded CPU sample (rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: skip the host-buffer leg")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="label exchange for --gpus > 1")
+    ap.add_argument("--gather", default="fused", choices=["fused", "push", "nccl"], help="label exchange for --gpus > 1")
     ap.add_argument("--no-multicast", action="store_true", help="fused exchange: per-peer stores instead of NVLS multicast")
     ap.add_argument("--wire", default="u8", choices=["u8", "i32"], help="label width of the fused exchange")
     ap.add_argument("--interleave", action="store_true", help="robustness check: run a cuBLAS GEMM between steps")

@@ -134,6 +134,10 @@ UML_API int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batc
  * Replaces kernel + ncclAllGather; the caller still needs one cross-rank barrier before reading peers' rows. */
 UML_API int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, void* const* peer_labels,
                              int n_peers, int64_t row_offset, int label_bytes, int mode, uml_stats* stats);
+/* second half of the two-step exchange: copy `bytes` of this rank's label slice (device memory) into each dst[i]
+ * (peer-mapped vectors, or one NVLS multicast alias that reaches every rank) on the engine stream.  Used after a
+ * uml_linear_predict_peers that targeted only the local vector, when a thin copy kernel beats in-epilogue stores. */
+UML_API int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst, int64_t bytes);
 /* end to end from HOST rows to HOST labels in one call (the /predict and Model.predict(features=...) shape): chunked
  * H2D, staging kernel, scoring kernel and label D2H pipelined on two streams; never holds more than a few chunks in
  * HBM.  host_ptr/labels_out may be pageable or pinned (uml_host_alloc). */

@@ -30,8 +30,9 @@ lo, hi = shard_bounds(N, rank, world); counts = shard_counts(N, world)
 b = eng.stage(X[lo:hi])
 got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True)            # NCCL all-gather
 torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy(), want), "nccl path"
-for dtype, mc in ((torch.int32, False), (torch.uint8, False), (torch.uint8, True), (torch.int32, True)):
-    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc)   # fused stores: per-peer or NVLS multicast
+for dtype, mc, push in ((torch.int32, False, False), (torch.uint8, False, False), (torch.uint8, True, False),
+                        (torch.int32, True, False), (torch.uint8, True, True), (torch.uint8, False, True)):
+    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc, push=push)   # fused stores / two-step push
     for _ in range(3):
         ex.labels.fill_(99); ex.barrier()
         got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True, exchange=ex)

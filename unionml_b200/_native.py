@@ -76,6 +76,7 @@ SIGNATURES = {
     "uml_batch_free": (None, [_P]),
     "uml_linear_predict": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(Stats)]),
     "uml_linear_predict_peers": (C.c_int, [_P, _P, _P, _PP, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(Stats)]),
+    "uml_labels_push": (C.c_int, [_P, _P, _PP, C.c_int, C.c_int64]),
     "uml_linear_predict_host": (
         C.c_int,
         [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int64, C.POINTER(Stats)],

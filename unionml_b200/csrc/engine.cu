@@ -11,6 +11,8 @@
 namespace uml {
 cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
                                cudaStream_t stream);
+cudaError_t launch_push_bytes(const void* src, void* const* dst, int n_dst, int64_t bytes, int sm_count,
+                              cudaStream_t stream);
 }
 
 using uml::FlagList;
@@ -728,6 +730,13 @@ int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch*
   if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
   // peer_labels[0] must be this rank's own vector (local target); labels land at peer_labels[i] + row_offset for all i
   return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, label_bytes, mode, stats);
+}
+
+int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst, int64_t bytes) {
+  if (!e || (!src && bytes > 0) || !dst || n_dst < 1 || n_dst > 8 || bytes < 0) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  UML_CUDA(e, uml::launch_push_bytes(src, dst, n_dst, bytes, e->info.sm_count, e->stream));
+  return UML_OK;
 }
 
 int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,

@@ -19,6 +19,7 @@
 #include "uml_common.cuh"
 #include "tma_ring.cuh"
 
+
 namespace uml {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -50,6 +51,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
   constexpr int CP = (C + 1 + 3) / 4 * 4;    // padded columns of wt in shared memory (layout shared by both modes)
   constexpr int NW4 = (NCOL + 3) / 4;        // float4 loads of W per feature
   constexpr int R = kRowsPerLane;
+  constexpr bool USE_F2 = EXACT;  // packed fp32x2 FMA where it measured faster (see the accumulator comment below)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1 KiB alignment
@@ -120,11 +122,26 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
       const int nv = static_cast<int>(min(static_cast<long long>(kConsumerWarps), (num_tiles - first + G - 1) / G));
       if (warp < nv) {
         const long long tile = first + warp * G;
-        float acc[R][NCOL];
+        // USE_F2 (EXACT kernels): class accumulators as fp32x2 pairs (classes 2i, 2i+1 -> one FFMA2, SASS FFMA2); an odd
+        // last class and the error-bound column (|x| is a free operand modifier on scalar FFMA) stay scalar.  Same-box
+        // A/B on 10M x 64 -> 10: EXACT 0.459 -> 0.397 ms with FFMA2, FAST 0.387 -> 0.416 ms (so FAST keeps scalar FFMA).
+        constexpr int NPAIR = C / 2;
+        constexpr bool ODD = (C & 1) != 0;
+        uint64_t acc2[R][NPAIR > 0 ? NPAIR : 1];
+        float acc_last[R], acc_bound[R];
+        float acc[R][C + 1];
 #pragma unroll
-        for (int j = 0; j < R; ++j)
+        for (int j = 0; j < R; ++j) {
+          if constexpr (USE_F2) {
 #pragma unroll
-          for (int c = 0; c < NCOL; ++c) acc[j][c] = bias_s[c];
+            for (int i = 0; i < NPAIR; ++i) acc2[j][i] = pack2(bias_s[2 * i], bias_s[2 * i + 1]);
+            acc_last[j] = ODD ? bias_s[C - 1] : 0.f;
+            acc_bound[j] = EXACT ? bias_s[C] : 0.f;
+          } else {
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) acc[j][c] = bias_s[c];
+          }
+        }
 
         for (int k = 0; k < KC; ++k) {
           const uint32_t seq = seq_base + static_cast<uint32_t>(k * nv + warp);
@@ -162,9 +179,17 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
 #pragma unroll
               for (int j = 0; j < R; ++j) {
                 const float x = e == 0 ? xv[j].x : e == 1 ? xv[j].y : e == 2 ? xv[j].z : xv[j].w;
+                if constexpr (USE_F2) {
+                  const uint64_t xx = pack2(x, x);
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[j][c] = fmaf(x, wv[c], acc[j][c]);
-                if (EXACT) acc[j][C] = fmaf(fabsf(x), wv[C], acc[j][C]);
+                  for (int i = 0; i < NPAIR; ++i) acc2[j][i] = fma2(xx, pack2(wv[2 * i], wv[2 * i + 1]), acc2[j][i]);
+                  if (ODD) acc_last[j] = fmaf(x, wv[C - 1], acc_last[j]);
+                  if (EXACT) acc_bound[j] = fmaf(fabsf(x), wv[C], acc_bound[j]);
+                } else {
+#pragma unroll
+                  for (int c = 0; c < C; ++c) acc[j][c] = fmaf(x, wv[c], acc[j][c]);
+                  if (EXACT) acc[j][C] = fmaf(fabsf(x), wv[C], acc[j][C]);
+                }
               }
             }
           }
@@ -172,11 +197,21 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
           if (lane == 0) mbar_arrive(&empty_bar[stage]);  // hand the stage back to the producer
         }
 
+        if constexpr (USE_F2) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) unpack2(acc2[j][i], acc[j][2 * i], acc[j][2 * i + 1]);
+            if (ODD) acc[j][C - 1] = acc_last[j];
+            acc[j][C] = acc_bound[j];
+          }
+        }
         // ---- fused epilogue: argmax (first maximum wins), margin guard, label store (+ peer stores) ----
+        const long long row0 = tile * kTileRows;
         int idxs[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          const long long row = tile * kTileRows + lane + 32 * j;
+          const long long row = row0 + lane + 32 * j;
           float best = acc[j][0];
           float second = -INFINITY;
           int idx = 0;
@@ -215,17 +250,17 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
           }
         }
         if (p.wire_u8 && p.n_peers > 0) {
-          // byte labels on the wire: transpose through shuffles so lane l holds rows 4l..4l+3 of the tile and the
-          // whole 128-row tile leaves as ONE coalesced 128-byte store per peer (instead of four int32 stores)
+          uint32_t word = 0;
+          // byte labels: transpose through shuffles so lane l holds rows 4l..4l+3 of the tile and the whole 128-row
+          // tile leaves as ONE coalesced 128-byte store per target (instead of four int32 stores)
           const uint32_t packed = static_cast<uint32_t>(idxs[0]) | (static_cast<uint32_t>(idxs[1]) << 8) |
                                   (static_cast<uint32_t>(idxs[2]) << 16) | (static_cast<uint32_t>(idxs[3]) << 24);
-          uint32_t word = 0;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint32_t w = __shfl_sync(0xffffffffu, packed, (4 * lane + t) & 31);
             word |= ((w >> (8 * (lane >> 3))) & 0xffu) << (8 * t);
           }
-          const long long row4 = tile * kTileRows + 4 * lane;
+          const long long row4 = row0 + 4 * lane;
           const long long at = p.row_offset + row4;
           if (row4 + 3 < p.n_rows && (at & 3) == 0) {
             for (int i = 0; i < p.n_peers; ++i)

@@ -105,6 +105,37 @@ __global__ void __launch_bounds__(256) finite_scan_kernel(const float* __restric
   if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
 }
 
+// dense variants (ld == F, source pitch == F): no per-element index arithmetic, 16-byte accesses
+__global__ void __launch_bounds__(256) finite_scan_dense_kernel(const float4* __restrict__ x, long long n4,
+                                                                StageResult* result) {
+  unsigned nonfinite = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    // x - x is 0 for finite x and NaN for NaN / Inf
+    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+    if (!(t == 0.f)) nonfinite = 1u;
+  }
+  if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_dense_kernel(const T* __restrict__ src, long long n, float* __restrict__ dst,
+                                                          double* __restrict__ dst64, StageResult* result) {
+  unsigned nonfinite = 0, lossy = 0;
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 o;
+    float* op = &o.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) convert_one(src[4 * i + k], op + k, dst64 ? dst64 + 4 * i + k : nullptr, nonfinite, lossy);
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+  if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicAdd(&result->nonfinite, 1ull);
+  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) atomicAdd(&result->lossy, 1ull);
+}
+
 template <typename T>
 static cudaError_t launch_typed(const void* src, bool feature_major, long long pitch, long long rows, int F, float* dst,
                                 long long ld, double* dst64, long long ld64, StageResult* result, cudaStream_t stream) {
@@ -113,6 +144,10 @@ static cudaError_t launch_typed(const void* src, bool feature_major, long long p
     const long long tiles = ((rows + 31) / 32) * ((ld + 31) / 32);
     const int grid = static_cast<int>(tiles < 148 * 16 ? (tiles < 1 ? 1 : tiles) : 148 * 16);
     stage_featmajor_kernel<T><<<grid, 256, 0, stream>>>(s, pitch, rows, F, dst, ld, dst64, ld64, result);
+  } else if (pitch == F && ld == F && (dst64 == nullptr || ld64 == F) && (F % 4) == 0) {
+    const long long want = (rows * ld / 4 + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+    stage_dense_kernel<T><<<grid, 256, 0, stream>>>(s, rows * ld, dst, dst64, result);
   } else {
     const long long total = rows * ld;
     const long long want = (total + 255) / 256;
@@ -143,9 +178,56 @@ cudaError_t launch_stage_convert(const void* src, int src_dtype, bool feature_ma
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// label push: copy this rank's slice of the label vector into the peers' vectors (or the NVLS multicast alias)
+// ---------------------------------------------------------------------------------------------------------------
+struct PushParams {
+  const unsigned char* src;
+  unsigned char* dst[8];
+  int n_dst;
+  long long bytes;
+};
+
+__global__ void __launch_bounds__(256) push_bytes_kernel(const PushParams p) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  bool aligned = (reinterpret_cast<uintptr_t>(p.src) & 15) == 0;
+  for (int d = 0; d < p.n_dst; ++d) aligned = aligned && (reinterpret_cast<uintptr_t>(p.dst[d]) & 15) == 0;
+  const long long n16 = aligned ? p.bytes / 16 : 0;
+  for (long long i = tid; i < n16; i += nthreads) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.src) + i);
+    for (int d = 0; d < p.n_dst; ++d) reinterpret_cast<uint4*>(p.dst[d])[i] = v;
+  }
+  for (long long i = n16 * 16 + tid; i < p.bytes; i += nthreads) {
+    const unsigned char v = p.src[i];
+    for (int d = 0; d < p.n_dst; ++d) p.dst[d][i] = v;
+  }
+}
+
+cudaError_t launch_push_bytes(const void* src, void* const* dst, int n_dst, int64_t bytes, int sm_count,
+                              cudaStream_t stream) {
+  if (bytes <= 0 || n_dst <= 0) return cudaSuccess;
+  PushParams p{};
+  p.src = static_cast<const unsigned char*>(src);
+  p.n_dst = n_dst;
+  for (int d = 0; d < 8; ++d) p.dst[d] = d < n_dst ? static_cast<unsigned char*>(dst[d]) : nullptr;
+  p.bytes = bytes;
+  const long long want = (bytes / 16 + 255) / 256;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want < sm_count ? want : sm_count));  // a thin kernel: <= 1 CTA per SM
+  push_bytes_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
                                cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
+  if (ld == n_features && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long n4 = rows * ld / 4;
+    const long long want4 = (n4 + 255) / 256;
+    const int grid4 = static_cast<int>(want4 < 148 * 32 ? (want4 < 1 ? 1 : want4) : 148 * 32);
+    finite_scan_dense_kernel<<<grid4, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n4, result);
+    return cudaGetLastError();
+  }
   const long long want = (rows * ld + 255) / 256;
   const int grid = static_cast<int>(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
   finite_scan_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, n_features, result);

@@ -313,6 +313,14 @@ class Engine:
         self._check(st)
         return stats.as_dict() if stats else None
 
+    def push_labels(self, src_ptr: int, dst_ptrs, nbytes: int) -> None:
+        """Copy ``nbytes`` from ``src_ptr`` (this rank's label slice) to every pointer in ``dst_ptrs`` (peer-mapped
+        vectors or an NVLS multicast alias) with a thin copy kernel on the engine stream."""
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(p) for p in dst_ptrs])
+        with self._lock:
+            st = N.lib().uml_labels_push(self._h, C.c_void_p(src_ptr), arr, len(dst_ptrs), nbytes)
+        self._check(st)
+
     def predict_host(
         self,
         model: LinearModel,

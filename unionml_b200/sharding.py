@@ -53,7 +53,7 @@ class PeerLabelExchange:
     """A full-length label vector (int32, or uint8 on the wire) in symmetric memory on every rank + peer pointers."""
 
     def __init__(self, total_rows: int, device: torch.device, group=None, dtype: torch.dtype = torch.int32,
-                 multicast: bool = True):
+                 multicast: bool = True, push: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
 
         if dtype not in (torch.int32, torch.uint8):
@@ -64,7 +64,9 @@ class PeerLabelExchange:
         self.handle = symm_mem.rendezvous(self.labels, self.group)
         self.rank = self.handle.rank
         self.world = self.handle.world_size
+        self.push = push  # two-step variant: kernel stores locally, a thin copy kernel pushes the slice to the peers
         ptrs = list(self.handle.buffer_ptrs)
+        self.own_ptr = ptrs[self.rank]
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
         self.multicast = mc != 0
         if self.multicast:
@@ -85,6 +87,13 @@ def predict_sharded(engine, model, batch, *, row_offset: int, counts: Sequence[i
                     group=None) -> torch.Tensor:
     """Score this rank's resident shard and return the full label vector (device tensor, identical on all ranks)."""
     rank = dist.get_rank(group)
+    if exchange is not None and exchange.push:
+        engine.predict_peers(model, batch, [exchange.own_ptr], row_offset, exact=exact, label_bytes=exchange.label_bytes)
+        off = row_offset * exchange.label_bytes
+        remote = exchange.peer_ptrs if exchange.multicast else exchange.peer_ptrs[1:]
+        engine.push_labels(exchange.own_ptr + off, [p + off for p in remote], counts[rank] * exchange.label_bytes)
+        exchange.barrier()
+        return exchange.labels
     if exchange is not None:
         engine.predict_peers(model, batch, exchange.peer_ptrs, row_offset, exact=exact, label_bytes=exchange.label_bytes)
         exchange.barrier()
