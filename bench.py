@@ -40,6 +40,9 @@ METRIC = "rows/sec batch predict (64->10 logistic)"
 UNIT = "rows/s"
 N_FEATURES = 64
 BYTES_PER_ROW = 4 * N_FEATURES  # algorithmic HBM read per row; + 4 B label write, not counted
+# dram__bytes_read.sum + dram__bytes_write.sum of one linear_argmax_tma launch on the default 10M x 64 batch, from the
+# committed `ncu --set full` capture (profiles/r01_linear_argmax_tma.ncu_raw.csv): 2.560199 GB + 7.15 MB
+NCU_TRAFFIC_BYTES_10M = 2_567_349_000
 
 
 def load_digits_model():
@@ -396,7 +399,8 @@ def run_gpu_arm(args):
         "peak_source": peak_src,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": args.traffic,
+        "traffic": args.traffic if args.traffic is not None else (NCU_TRAFFIC_BYTES_10M if rows == 10_000_000 else None),
+        "traffic_source": "profiles/r01_linear_argmax_tma.ncu_raw.csv (ncu --set full, per launch)",
         "kernel_ms": kernel_ms,
         "kernel_ms_min": min(k_ms),
         "rescore_ms": statistics.mean(r_ms),
