@@ -345,3 +345,23 @@ def test_feature_array_borrowing():
     sliced = np.arange(64, dtype=np.float32).reshape(8, 8)[::2, ::2]
     assert as_feature_array(sliced).flags.c_contiguous
     assert olin.validate_features(as_feature_array(sliced), 4).shape == (4, 4)
+
+
+def test_cli_serve_sets_model_path_and_starts_uvicorn(monkeypatch, tmp_path):
+    """`serve` = uvicorn + --model-path exported as UNIONML_MODEL_PATH (ref. cli.py:285-320)."""
+    import uvicorn
+
+    from unionml_b200 import cli
+
+    calls = {}
+    monkeypatch.setattr(uvicorn, "run", lambda app, **kw: calls.update(app=app, **kw))
+    model_file = tmp_path / "m.joblib"
+    model_file.write_bytes(b"x")
+    monkeypatch.delenv("UNIONML_MODEL_PATH", raising=False)
+    assert cli.main(["serve", "app:app", "--model-path", str(model_file), "--port", "8123"]) == 0
+    import os
+
+    assert os.environ["UNIONML_MODEL_PATH"] == str(model_file)
+    assert calls["app"] == "app:app" and calls["port"] == 8123
+    with pytest.raises(SystemExit):
+        cli.main(["serve", "app:app", "--model-path", str(tmp_path / "missing.joblib")])

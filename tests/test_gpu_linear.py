@@ -320,3 +320,75 @@ def test_ring_protocol_with_foreign_kernels_between_launches(tmp_path, stages):
         env["UML_B200_STAGES"] = stages
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ring ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the README digits app end to end on the device path (BASELINE.json configs[0] and [3])
+# ---------------------------------------------------------------------------------------------------------------
+def test_digits_app_and_fastapi_on_the_device_path(tmp_path, monkeypatch):
+    from typing import List
+
+    from fastapi import FastAPI
+    from fastapi.testclient import TestClient
+    from sklearn.datasets import load_digits
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.metrics import accuracy_score
+
+    from unionml_b200 import Dataset, Model
+    from unionml_b200.predictors import linear_argmax
+
+    def make_app():
+        dataset = Dataset(name="digits_dataset", test_size=0.2, shuffle=True, targets=["target"])
+        model = Model(name="digits_classifier", init=LogisticRegression, dataset=dataset)
+
+        @dataset.reader
+        def reader() -> pd.DataFrame:
+            return load_digits(as_frame=True).frame
+
+        @model.trainer
+        def trainer(estimator: LogisticRegression, features: pd.DataFrame, target: pd.DataFrame) -> LogisticRegression:
+            return estimator.fit(features, target.squeeze())
+
+        seen = []
+
+        def monitor(estimator: LogisticRegression, features: pd.DataFrame, predictions: List[float]):
+            seen.append(len(predictions))
+
+        @model.predictor(callbacks=[monitor])
+        def predictor(estimator: LogisticRegression, features: pd.DataFrame) -> List[float]:
+            return linear_argmax(estimator, features)  # the one changed line of the README app
+
+        @model.evaluator
+        def evaluator(estimator: LogisticRegression, features: pd.DataFrame, target: pd.DataFrame) -> float:
+            return float(accuracy_score(target.squeeze(), predictor(estimator, features)))
+
+        return model, seen
+
+    model, seen = make_app()
+    est, metrics = model.train(hyperparameters={"C": 1.0, "max_iter": 1000})
+    # evaluator ran the GPU predictor on both splits: same metrics as the CPU pipeline (SURVEY.md 8d cfg 1)
+    assert metrics["train"] == 1.0 and abs(metrics["test"] - 0.9639) < 1e-3
+    frame = load_digits(as_frame=True).frame
+    feats = frame[[c for c in frame if c != "target"]]
+    assert model.predict(features=feats.sample(3, random_state=99)) == [8.0, 8.0, 0.0]
+    assert model.predict(features=frame.sample(5, random_state=42)) == [6.0, 9.0, 3.0, 7.0, 2.0]
+    whole = model.predict()  # reader path
+    assert whole == [float(x) for x in est.predict(feats)] and seen[-1] == len(frame)
+
+    path = tmp_path / "model.joblib"
+    model.save(path)
+    served, _ = make_app()
+    app = FastAPI()
+    served.serve(app)
+    monkeypatch.setenv("UNIONML_MODEL_PATH", str(path))
+    with TestClient(app) as client:
+        assert client.get("/health").status_code == 200
+        r = client.post("/predict", json={"features": feats.sample(32, random_state=7).to_dict(orient="records")})
+        assert r.status_code == 200
+        assert r.json() == [float(x) for x in est.predict(feats.sample(32, random_state=7))]
+        # reordered / missing columns -> the same ValueError sklearn raises, surfaced as a server error
+        bad = feats.sample(2, random_state=1).iloc[:, ::-1].to_dict(orient="records")
+        ok = client.post("/predict", json={"features": bad})  # the feature loader re-selects columns by name: still fine
+        assert ok.status_code == 200
+    with pytest.raises(ValueError, match="feature names"):
+        linear_argmax(est, feats.iloc[:4, ::-1])
