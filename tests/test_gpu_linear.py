@@ -372,7 +372,9 @@ def test_digits_app_and_fastapi_on_the_device_path(tmp_path, monkeypatch):
     feats = frame[[c for c in frame if c != "target"]]
     assert model.predict(features=feats.sample(3, random_state=99)) == [8.0, 8.0, 0.0]
     assert model.predict(features=frame.sample(5, random_state=42)) == [6.0, 9.0, 3.0, 7.0, 2.0]
-    whole = model.predict()  # reader path
+    with pytest.raises(ValueError, match="At least one of features"):  # no-arg reader: same guard as ref. model.py:727
+        model.predict()
+    whole = model.predict(features=frame)  # the feature loader drops the target column (dataset.py:515-518)
     assert whole == [float(x) for x in est.predict(feats)] and seen[-1] == len(frame)
 
     path = tmp_path / "model.joblib"
@@ -386,9 +388,10 @@ def test_digits_app_and_fastapi_on_the_device_path(tmp_path, monkeypatch):
         r = client.post("/predict", json={"features": feats.sample(32, random_state=7).to_dict(orient="records")})
         assert r.status_code == 200
         assert r.json() == [float(x) for x in est.predict(feats.sample(32, random_state=7))]
-        # reordered / missing columns -> the same ValueError sklearn raises, surfaced as a server error
+        # reordered columns: the default feature loader keeps the request's order, and the predictor raises the same
+        # ValueError sklearn raises (utils/validation.py:2769); TestClient re-raises server exceptions
         bad = feats.sample(2, random_state=1).iloc[:, ::-1].to_dict(orient="records")
-        ok = client.post("/predict", json={"features": bad})  # the feature loader re-selects columns by name: still fine
-        assert ok.status_code == 200
+        with pytest.raises(ValueError, match="feature names"):
+            client.post("/predict", json={"features": bad})
     with pytest.raises(ValueError, match="feature names"):
         linear_argmax(est, feats.iloc[:4, ::-1])
