@@ -19,6 +19,12 @@
 #include "uml_common.cuh"
 #include "tma_ring.cuh"
 
+#ifndef UML_MLP_UNROLL_Q
+#define UML_MLP_UNROLL_Q 8  // feature-quad unroll of the layer-1 loop (same-box A/B, EXACT: 1 -> 1.120, 2 -> 1.056, 4 -> 1.023, 8 -> 1.015 ms)
+#endif
+#define UML_PRAGMA_(x) _Pragma(#x)
+#define UML_UNROLL(n) UML_PRAGMA_(unroll n)
+
 namespace uml {
 
 // 8 consumer warps work as 4 PAIRS: a pair shares one 128-row x 32-feature box, warp 2p takes rows 0..63 and warp 2p+1
@@ -138,7 +144,7 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
           mbar_wait(&full_bar[stage], phase);
           const uint8_t* xs = smem + static_cast<size_t>(stage) * kMlpStageBytes;
           const float* wk = w1_s + k * kChunkF * HP;
-#pragma unroll 2
+          UML_UNROLL(UML_MLP_UNROLL_Q)
           for (int q = 0; q < kChunkF / 4; ++q) {
             float4 xv[R];
             const uint32_t off = lanebase ^ static_cast<uint32_t>(q * 16);
