@@ -86,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -103,7 +103,7 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -371,6 +371,13 @@ def run_gpu_arm(args):
         flagged = st["n_flagged"]
         launches_per_step = st["kernel_launches"]
     kernel_ms = statistics.mean(k_ms)
+    # the timed region lasts only K x 0.4 ms; keep the same load running (untimed) until nvidia-smi has had ~0.6 s to
+    # sample clocks / throttle reasons under it
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
     exchange_ms = None
     if world > 1:  # cost of the label exchange alone (barrier or all-gather), CUDA events, same stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -465,7 +472,16 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, times = cpu_reference_predict_rows_per_s(args.cpu_rows, 3)
         cores = blas_threads()
+        est_nd = sklearn_estimator()
+        Xnd = X_host[: args.cpu_rows].astype(np.float64)
+        nd_t = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            est_nd.predict(Xnd)
+            nd_t.append(time.perf_counter() - t0)
         cpu_baseline = {
+            "ndarray_value": args.cpu_rows / min(nd_t),
+            "ndarray_note": "bare LogisticRegression.predict on a C-order float64 ndarray (no DataFrame, no list conversion)",
             "value": rps,
             "unit": UNIT,
             "cores": cores,
