@@ -97,6 +97,9 @@ UML_API int uml_engine_synchronize(uml_engine* e);
 /* pinned host memory for feature frames / label vectors (what `bench.py` e2e and the serving path stage through) */
 UML_API int uml_host_alloc(uml_engine* e, void** out, int64_t bytes);
 UML_API int uml_host_free(uml_engine* e, void* p);
+/* plain device memory (label vectors for callers that do not bring their own allocator) */
+UML_API int uml_device_alloc(uml_engine* e, void** out, int64_t bytes);
+UML_API int uml_device_free(uml_engine* e, void* p);
 
 /* ---- model: where W, b come from - joblib.load(file)["model_obj"].coef_/intercept_ (model.py:1498-1500) -------- */
 /* coef: n_classes x n_features row-major (sklearn coef_; a binary model passes its single row with n_classes = 1 and
@@ -134,6 +137,15 @@ UML_API int uml_linear_predict(uml_engine* e, const uml_model* m, const uml_batc
  * Replaces kernel + ncclAllGather; the caller still needs one cross-rank barrier before reading peers' rows. */
 UML_API int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch* b, void* const* peer_labels,
                              int n_peers, int64_t row_offset, int label_bytes, int mode, uml_stats* stats);
+/* label post-processing on the device (labels_dev: int32 or uint8 class indices in device memory):
+ * uml_labels_take        - classes_.take(indices) (sklearn/linear_model/_base.py:423) + the float conversion of the
+ *                          canonical predictor (README.md:92): out_host[i] = classes_host[label[i]] as float64;
+ * uml_labels_count_equal - rows whose predicted class value equals targets_host[i]: the numerator of the reference
+ *                          evaluator's accuracy_score (README.md:94-100). */
+UML_API int uml_labels_take(uml_engine* e, const void* labels_dev, int label_bytes, int64_t n, const double* classes_host,
+                    int n_classes, double* out_host);
+UML_API int uml_labels_count_equal(uml_engine* e, const void* labels_dev, int label_bytes, int64_t n,
+                           const double* classes_host, int n_classes, const double* targets_host, int64_t* count_out);
 /* second half of the two-step exchange: copy `bytes` of this rank's label slice (device memory) into each dst[i]
  * (peer-mapped vectors, or one NVLS multicast alias that reaches every rank) on the engine stream.  Used after a
  * uml_linear_predict_peers that targeted only the local vector, when a thin copy kernel beats in-epilogue stores. */

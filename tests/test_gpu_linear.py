@@ -395,3 +395,32 @@ def test_digits_app_and_fastapi_on_the_device_path(tmp_path, monkeypatch):
             client.post("/predict", json={"features": bad})
     with pytest.raises(ValueError, match="feature names"):
         linear_argmax(est, feats.iloc[:4, ::-1])
+
+
+def test_device_side_take_and_accuracy(engine, digits_model):
+    """classes_.take + float conversion and the evaluator's match count on the device."""
+    from sklearn.linear_model import LogisticRegression
+
+    from unionml_b200.predictors import linear_accuracy
+
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    classes = np.array([3.0, 1.5, -2.0, 7.0, 9.0, 11.0, 0.0, 4.0, 5.0, 6.0])  # not the identity map
+    m = engine.load_linear(coef, intercept)
+    X = digits_rows(21, 200_001)
+    idx = oracle_idx(X, coef, intercept)
+    b = engine.stage(X)
+    buf = engine.device_alloc(4 * b.n_rows)
+    engine.predict(m, b, exact=True, out_device_ptr=buf.ptr, want_stats=True)
+    got = engine.take_labels(buf.ptr, b.n_rows, classes)
+    np.testing.assert_array_equal(got, classes[idx])
+    target = classes[idx].copy()
+    target[::7] += 100.0  # 1/7 of the rows are "wrong"
+    hits = engine.count_equal(buf.ptr, b.n_rows, classes, target)
+    assert hits == int((classes[idx] == target).sum())
+    est = LogisticRegression()
+    est.coef_, est.intercept_, est.classes_, est.n_features_in_ = coef, intercept, classes, 64
+    assert linear_accuracy(est, X, target) == hits / b.n_rows
+    # uint8 label vectors go through the same kernels
+    u8 = engine.device_alloc(b.n_rows)
+    engine.predict_peers(m, b, [u8.ptr], 0, exact=True, want_stats=True, label_bytes=1)
+    np.testing.assert_array_equal(engine.take_labels(u8.ptr, b.n_rows, classes, label_bytes=1), classes[idx])

@@ -64,6 +64,8 @@ SIGNATURES = {
     "uml_engine_synchronize": (C.c_int, [_P]),
     "uml_host_alloc": (C.c_int, [_P, _PP, C.c_int64]),
     "uml_host_free": (C.c_int, [_P, _P]),
+    "uml_device_alloc": (C.c_int, [_P, _PP, C.c_int64]),
+    "uml_device_free": (C.c_int, [_P, _P]),
     "uml_linear_load": (C.c_int, [_P, _PP, _P, _P, C.c_int, C.c_int, C.c_int]),
     "uml_model_free": (None, [_P]),
     "uml_linear_set_affine": (C.c_int, [_P, _P, _P, _P]),
@@ -76,6 +78,8 @@ SIGNATURES = {
     "uml_batch_free": (None, [_P]),
     "uml_linear_predict": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(Stats)]),
     "uml_linear_predict_peers": (C.c_int, [_P, _P, _P, _PP, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(Stats)]),
+    "uml_labels_take": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, _P]),
+    "uml_labels_count_equal": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, _P, C.POINTER(C.c_int64)]),
     "uml_labels_push": (C.c_int, [_P, _P, _PP, C.c_int, C.c_int64]),
     "uml_linear_predict_host": (
         C.c_int,

@@ -13,6 +13,11 @@ cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_f
                                cudaStream_t stream);
 cudaError_t launch_push_bytes(const void* src, void* const* dst, int n_dst, int64_t bytes, int sm_count,
                               cudaStream_t stream);
+cudaError_t launch_labels_take(const void* labels, int label_bytes, int64_t n, const double* classes, int n_classes,
+                               double* out, cudaStream_t stream);
+cudaError_t launch_labels_count_equal(const void* labels, int label_bytes, int64_t n, const double* classes,
+                                      int n_classes, const double* targets, unsigned long long* count,
+                                      cudaStream_t stream);
 }
 
 using uml::FlagList;
@@ -232,6 +237,20 @@ int uml_host_alloc(uml_engine* e, void** out, int64_t bytes) {
   if (!e || !out || bytes < 0) return UML_ERR_INVALID;
   UML_CUDA(e, cudaSetDevice(e->device));
   UML_CUDA(e, cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+  return UML_OK;
+}
+
+int uml_device_alloc(uml_engine* e, void** out, int64_t bytes) {
+  if (!e || !out || bytes < 0) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  UML_CUDA(e, cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 1)));
+  return UML_OK;
+}
+
+int uml_device_free(uml_engine* e, void* p) {
+  if (!e) return UML_ERR_INVALID;
+  UML_CUDA(e, cudaSetDevice(e->device));
+  if (p) UML_CUDA(e, cudaFree(p));
   return UML_OK;
 }
 
@@ -730,6 +749,75 @@ int uml_linear_predict_peers(uml_engine* e, const uml_model* m, const uml_batch*
   if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
   // peer_labels[0] must be this rank's own vector (local target); labels land at peer_labels[i] + row_offset for all i
   return predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, label_bytes, mode, stats);
+}
+
+// labels (device, int32 or uint8 indices) -> classes_[idx] as float64 in HOST memory: the device-side classes_.take of
+// sklearn/linear_model/_base.py:423 followed by the float conversion of the canonical predictor (README.md:92)
+int uml_labels_take(uml_engine* e, const void* labels_dev, int label_bytes, int64_t n, const double* classes_host,
+                    int n_classes, double* out_host) {
+  if (!e || (!labels_dev && n > 0) || !classes_host || n_classes < 1 || (!out_host && n > 0) || n < 0) return UML_ERR_INVALID;
+  if (label_bytes != 1 && label_bytes != 4) UML_FAIL(e, UML_ERR_INVALID, "label_bytes %d", label_bytes);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  if (n == 0) return UML_OK;
+  double* d_classes = nullptr;
+  double* d_out = nullptr;
+  UML_CUDA(e, cudaMalloc((void**)&d_classes, (size_t)n_classes * 8));
+  cudaError_t ce = cudaMalloc((void**)&d_out, (size_t)n * 8);
+  if (ce != cudaSuccess) {
+    cudaFree(d_classes);
+    UML_FAIL(e, UML_ERR_NOMEM, "uml_labels_take: %s", cudaGetErrorString(ce));
+  }
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_classes);
+    cudaFree(d_out);
+    return rc;
+  };
+  if ((ce = cudaMemcpyAsync(d_classes, classes_host, (size_t)n_classes * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess ||
+      (ce = uml::launch_labels_take(labels_dev, label_bytes, n, d_classes, n_classes, d_out, e->stream)) != cudaSuccess ||
+      (ce = cudaMemcpyAsync(out_host, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess ||
+      (ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) {
+    e->last_error = std::string("uml_labels_take: ") + cudaGetErrorString(ce);
+    return done(UML_ERR_CUDA);
+  }
+  return done(UML_OK);
+}
+
+// number of rows whose predicted class value equals the target (the numerator of accuracy_score in the reference's
+// evaluator, README.md:94-100); targets are float64 in HOST memory
+int uml_labels_count_equal(uml_engine* e, const void* labels_dev, int label_bytes, int64_t n, const double* classes_host,
+                           int n_classes, const double* targets_host, int64_t* count_out) {
+  if (!e || (!labels_dev && n > 0) || !classes_host || n_classes < 1 || (!targets_host && n > 0) || !count_out || n < 0)
+    return UML_ERR_INVALID;
+  if (label_bytes != 1 && label_bytes != 4) UML_FAIL(e, UML_ERR_INVALID, "label_bytes %d", label_bytes);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  *count_out = 0;
+  if (n == 0) return UML_OK;
+  double* d_classes = nullptr;
+  double* d_targets = nullptr;
+  UML_CUDA(e, cudaMalloc((void**)&d_classes, (size_t)n_classes * 8));
+  cudaError_t ce = cudaMalloc((void**)&d_targets, (size_t)n * 8);
+  if (ce != cudaSuccess) {
+    cudaFree(d_classes);
+    UML_FAIL(e, UML_ERR_NOMEM, "uml_labels_count_equal: %s", cudaGetErrorString(ce));
+  }
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_classes);
+    cudaFree(d_targets);
+    return rc;
+  };
+  if ((ce = cudaMemcpyAsync(d_classes, classes_host, (size_t)n_classes * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess ||
+      (ce = cudaMemcpyAsync(d_targets, targets_host, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess ||
+      (ce = cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream)) != cudaSuccess ||
+      (ce = uml::launch_labels_count_equal(labels_dev, label_bytes, n, d_classes, n_classes, d_targets, e->d_counters, e->stream)) != cudaSuccess ||
+      (ce = cudaMemcpyAsync(e->h->counters, e->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess ||
+      (ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) {
+    e->last_error = std::string("uml_labels_count_equal: ") + cudaGetErrorString(ce);
+    return done(UML_ERR_CUDA);
+  }
+  *count_out = (int64_t)e->h->counters[0];
+  return done(UML_OK);
 }
 
 int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst, int64_t bytes) {

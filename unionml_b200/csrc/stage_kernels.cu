@@ -218,6 +218,55 @@ cudaError_t launch_push_bytes(const void* src, void* const* dst, int n_dst, int6
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// label post-processing: classes_.take on the device and the evaluator's match count
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) labels_take_kernel(const void* __restrict__ labels, int label_bytes, long long n,
+                                                          const double* __restrict__ classes, int n_classes,
+                                                          double* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int idx = label_bytes == 1 ? static_cast<int>(static_cast<const unsigned char*>(labels)[i])
+                                     : static_cast<const int*>(labels)[i];
+    out[i] = idx >= 0 && idx < n_classes ? __ldg(classes + idx) : nan("");
+  }
+}
+
+__global__ void __launch_bounds__(256) labels_count_equal_kernel(const void* __restrict__ labels, int label_bytes,
+                                                                 long long n, const double* __restrict__ classes,
+                                                                 int n_classes, const double* __restrict__ targets,
+                                                                 unsigned long long* count) {
+  unsigned long long local = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int idx = label_bytes == 1 ? static_cast<int>(static_cast<const unsigned char*>(labels)[i])
+                                     : static_cast<const int*>(labels)[i];
+    if (idx >= 0 && idx < n_classes && __ldg(classes + idx) == targets[i]) ++local;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+cudaError_t launch_labels_take(const void* labels, int label_bytes, int64_t n, const double* classes, int n_classes,
+                               double* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const long long want = (n + 255) / 256;
+  const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  labels_take_kernel<<<grid, 256, 0, stream>>>(labels, label_bytes, n, classes, n_classes, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_labels_count_equal(const void* labels, int label_bytes, int64_t n, const double* classes,
+                                      int n_classes, const double* targets, unsigned long long* count,
+                                      cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const long long want = (n + 255) / 256;
+  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  labels_count_equal_kernel<<<grid, 256, 0, stream>>>(labels, label_bytes, n, classes, n_classes, targets, count);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
                                cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;

@@ -132,6 +132,14 @@ class Batch:
         self._fin()
 
 
+class DeviceBuffer:
+    """``nbytes`` of device memory from ``uml_device_alloc``."""
+
+    def __init__(self, engine: "Engine", ptr: int, nbytes: int):
+        self.engine, self.ptr, self.nbytes = engine, ptr, nbytes
+        self._fin = weakref.finalize(self, N.lib().uml_device_free, engine._h, ptr)
+
+
 class Engine:
     """One CUDA device bound to this process (one process per GPU)."""
 
@@ -186,6 +194,12 @@ class Engine:
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
         weakref.finalize(buf, N.lib().uml_host_free, self._h, p.value)
         return arr
+
+    def device_alloc(self, nbytes: int) -> "DeviceBuffer":
+        """Plain device memory owned by a small handle object (freed when it is garbage collected)."""
+        p = C.c_void_p()
+        self._check(N.lib().uml_device_alloc(self._h, C.byref(p), int(nbytes)))
+        return DeviceBuffer(self, p.value, int(nbytes))
 
     # ------------------------------------------------------------------------------------------------------------
     def load_linear(self, coef, intercept, classes=None) -> LinearModel:
@@ -312,6 +326,30 @@ class Engine:
             )
         self._check(st)
         return stats.as_dict() if stats else None
+
+    def take_labels(self, labels_ptr: int, n: int, classes, label_bytes: int = 4) -> np.ndarray:
+        """``classes_[idx].astype(float)`` computed on the device from a device label vector; float64 host array."""
+        classes = np.ascontiguousarray(classes, dtype=np.float64)
+        out = np.empty(n, dtype=np.float64)
+        with self._lock:
+            st = N.lib().uml_labels_take(self._h, C.c_void_p(labels_ptr), label_bytes, n,
+                                         classes.ctypes.data_as(C.c_void_p), len(classes), out.ctypes.data_as(C.c_void_p))
+        self._check(st)
+        return out
+
+    def count_equal(self, labels_ptr: int, n: int, classes, targets, label_bytes: int = 4) -> int:
+        """Number of rows whose predicted class value equals ``targets`` (accuracy numerator), reduced on the device."""
+        classes = np.ascontiguousarray(classes, dtype=np.float64)
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        if targets.shape != (n,):
+            raise ValueError("targets must be a vector of length n")
+        cnt = C.c_int64()
+        with self._lock:
+            st = N.lib().uml_labels_count_equal(self._h, C.c_void_p(labels_ptr), label_bytes, n,
+                                                classes.ctypes.data_as(C.c_void_p), len(classes),
+                                                targets.ctypes.data_as(C.c_void_p), C.byref(cnt))
+        self._check(st)
+        return int(cnt.value)
 
     def push_labels(self, src_ptr: int, dst_ptrs, nbytes: int) -> None:
         """Copy ``nbytes`` from ``src_ptr`` (this rank's label slice) to every pointer in ``dst_ptrs`` (peer-mapped

@@ -91,6 +91,26 @@ def linear_predict_labels(estimator, features, exact: bool | None = None, engine
     return np.asarray(classes).take(idx, axis=0)
 
 
+def linear_accuracy(estimator: Any, features: Any, target: Any, exact: bool | None = None) -> float:
+    """``accuracy_score(target, estimator.predict(features))`` for numeric class labels, with the predict, the
+    ``classes_.take`` and the match count all on the device (the reference evaluator, ``README.md:94-100``, runs the
+    predictor and compares Python lists)."""
+    engine = get_engine()
+    dm = device_model(estimator, engine)
+    _check_feature_names(estimator, features)
+    batch = engine.stage(features)
+    labels = engine.device_alloc(4 * max(batch.n_rows, 1))
+    engine.predict(dm, batch, exact=_exact_default() if exact is None else exact, out_device_ptr=labels.ptr,
+                   want_stats=True)  # stats: synchronises and raises on NaN/Inf like sklearn
+    y = np.asarray(target.to_numpy() if hasattr(target, "to_numpy") else target, dtype=np.float64).reshape(-1)
+    if y.shape[0] != batch.n_rows:
+        raise ValueError(f"Found input variables with inconsistent numbers of samples: [{y.shape[0]}, {batch.n_rows}]")
+    classes = np.asarray(getattr(estimator, "classes_", np.arange(dm.n_classes)), dtype=np.float64)
+    hits = engine.count_equal(labels.ptr, batch.n_rows, classes, y)
+    batch.free()
+    return hits / max(batch.n_rows, 1)
+
+
 def linear_argmax(estimator: Any, features: Any) -> List[float]:
     """Drop-in body for ``@model.predictor``: class labels as Python floats."""
     return linear_predict_labels(estimator, features).astype(np.float64).tolist()
