@@ -1,9 +1,16 @@
-"""Logger ``unionml_b200`` (the reference logs through ``logging.getLogger("unionml")``, ``unionml/_logging.py:3-7``)."""
+"""Package logger.  The reference logs through ``logging.getLogger("unionml")`` at INFO with a stream handler
+(``unionml/_logging.py``); callback failures on the predict path are reported here and never propagated."""
 import logging
 
-logger = logging.getLogger("unionml_b200")
-if not logger.handlers:
-    _h = logging.StreamHandler()
-    _h.setFormatter(logging.Formatter("%(asctime)s %(name)s %(levelname)s %(message)s"))
-    logger.addHandler(_h)
-logger.setLevel(logging.INFO)
+
+def _make_logger() -> logging.Logger:
+    log = logging.getLogger("unionml_b200")
+    log.setLevel(logging.INFO)
+    if not any(isinstance(h, logging.StreamHandler) for h in log.handlers):
+        handler = logging.StreamHandler()
+        handler.setFormatter(logging.Formatter("%(asctime)s %(name)s %(levelname)s %(message)s"))
+        log.addHandler(handler)
+    return log
+
+
+logger = _make_logger()

@@ -175,43 +175,51 @@ class Dataset:
         return self._feature_transformer(self._feature_loader(features))
 
     # ---------------------------------------------------------------------------------------------------------
-    # defaults (ref. dataset.py:472-527)
+    # defaults (behaviour of ref. dataset.py:472-527; pandas frames are the only structure handled natively)
     # ---------------------------------------------------------------------------------------------------------
+    def _frames_are_native(self) -> bool:
+        return self.dataset_datatype["data"] is pd.DataFrame
+
     def _default_loader(self, data: Any) -> Any:
-        if self.dataset_datatype["data"] is pd.DataFrame:
-            return pd.DataFrame(data)
-        return data
+        return pd.DataFrame(data) if self._frames_are_native() else data
 
     def _default_splitter(self, data: Any, test_size: float, shuffle: bool, random_state: int) -> Tuple[Any, ...]:
-        if not isinstance(data, pd.DataFrame):
-            return (data,)
-        from sklearn.model_selection import train_test_split
+        if isinstance(data, pd.DataFrame):
+            from sklearn.model_selection import train_test_split
 
-        return tuple(train_test_split(data, test_size=test_size, random_state=random_state, shuffle=shuffle))
+            train, test = train_test_split(data, test_size=test_size, random_state=random_state, shuffle=shuffle)
+            return train, test
+        return (data,)
 
     def _default_parser(self, data: Any, features: Optional[List[str]], targets: Optional[List[str]]) -> Tuple[Any, ...]:
         if not isinstance(data, pd.DataFrame):
             return (data,)
-        # quirk kept on purpose (ref. 498-499): an explicit feature list is replaced by "every non-target column"
+        # Quirk kept on purpose (ref. 498-499): whenever a target list exists, an explicit feature list is replaced by
+        # "every column that is not a target".
+        feature_cols = features
         if features is not None and targets is not None:
-            features = [col for col in data if col not in targets]
-        try:
-            target_data = data[targets]
-        except KeyError:
-            target_data = pd.DataFrame()
-        return data[features], target_data
+            feature_cols = [c for c in data.columns if c not in targets]
+        target_frame = data[targets] if _has_columns(data, targets) else pd.DataFrame()
+        return data[feature_cols], target_frame
 
     def _default_feature_loader(self, features: Any) -> Any:
-        if isinstance(features, Path):
-            with features.open() as f:
-                features = json.load(f)
-        if self.dataset_datatype["data"] is pd.DataFrame:
-            data = pd.DataFrame(features)
-            names = self._features
-            if not names and self._targets is not None:
-                names = [col for col in data if col not in self._targets]
-            return data[names]
-        return features
+        raw = json.loads(features.read_text()) if isinstance(features, Path) else features
+        if not self._frames_are_native():
+            return raw
+        frame = pd.DataFrame(raw)
+        wanted = self._features
+        if not wanted and self._targets is not None:
+            wanted = [c for c in frame.columns if c not in self._targets]
+        return frame[wanted]
 
     def _default_feature_transformer(self, features: Any) -> Any:
-        return features
+        return features  # identity unless @dataset.feature_transformer is registered
+
+
+def _has_columns(frame: pd.DataFrame, names: Optional[List[str]]) -> bool:
+    """``frame[names]`` would succeed (the reference catches the KeyError instead, ref. 500-503)."""
+    try:
+        frame[names]
+        return True
+    except KeyError:
+        return False

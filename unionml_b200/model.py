@@ -161,25 +161,26 @@ class Model:
         """Register the function behind the drop-in boundary (ref. ``model.py:319-367``)."""
         if fn is None:
             return partial(self.predictor, callbacks=callbacks, **predict_task_kwargs)
-        type_guards.guard_predictor(fn, self.model_type, self._dataset.feature_type)
+        model_t, feature_t = self.model_type, self._dataset.feature_type
+        type_guards.guard_predictor(fn, model_t, feature_t)
         self._predictor = fn
         self._predict_task_kwargs = dict(predict_task_kwargs)
+        # callbacks are checked against the predictor's return annotation, so they are validated after it
+        checked = []
+        for cb in callbacks or ():
+            if not callable(cb):
+                raise ValueError("Callback must be a callable function.")
+            type_guards.guard_prediction_callback(
+                callback=cb, predictor=fn, expected_model_type=model_t, expected_data_type=feature_t
+            )
+            checked.append(cb)
         if callbacks is not None:
-            for cb in callbacks:
-                if not callable(cb):
-                    raise ValueError("Callback must be a callable function.")
-                type_guards.guard_prediction_callback(
-                    predictor=fn,
-                    callback=cb,
-                    expected_model_type=self.model_type,
-                    expected_data_type=self._dataset.feature_type,
-                )
-            self.predict_callbacks = tuple(callbacks)
-        if not hasattr(fn, "__unionml_model__"):
-            try:
-                fn.__unionml_model__ = self
-            except AttributeError:  # builtins / bound methods
-                pass
+            self.predict_callbacks = checked
+        try:
+            if not hasattr(fn, "__unionml_model__"):
+                fn.__unionml_model__ = self  # lets decorators stacked on top find the model
+        except AttributeError:  # builtins / bound methods do not take attributes
+            pass
         return fn
 
     def evaluator(self, fn):
@@ -282,21 +283,23 @@ class Model:
         model_file: Optional[Union[str, os.PathLike]] = None,
         loader_kwargs: Optional[dict] = None,
     ) -> ModelArtifact:
-        if sum(x is not None for x in (model_object, model_version, model_file)) > 1:
+        sources = {"model_object": model_object, "model_version": model_version, "model_file": model_file}
+        given = [k for k, v in sources.items() if v is not None]
+        if len(given) > 1:
             raise ValueError("You can specify only one of 'model_object', 'model_version', or 'model_file' arguments.")
-        if model_object is not None:
-            return ModelArtifact(model_object)
-        if model_version is not None:
-            raise NotImplementedError("Fetching artifacts from a Flyte cluster is out of scope for unionml_b200.")
-        if model_file is not None:
-            return ModelArtifact(self.load(model_file, **(loader_kwargs or {})))
-        if self.artifact is not None:
+        if not given:
+            if self.artifact is None:
+                raise ValueError(
+                    "Model object not found. Make sure to specify at least one of model_version, model_file, or "
+                    "model_object. Alternatively, train a model locally with the .train(...) method so the "
+                    "model.artifact property contains a model object."
+                )
             return self.artifact
-        raise ValueError(
-            "Model object not found. Make sure to specify at least one of model_version, model_file, or "
-            "model_object. Alternatively, train a model locally with the .train(...) method so the model.artifact "
-            "property contains a model object."
-        )
+        if given[0] == "model_object":
+            return ModelArtifact(model_object)
+        if given[0] == "model_file":
+            return ModelArtifact(self.load(model_file, **(loader_kwargs or {})))
+        raise NotImplementedError("Fetching artifacts from a Flyte cluster is out of scope for unionml_b200.")
 
     def _default_init(self, hyperparameters: dict) -> Any:
         if self._init_callable is None:
