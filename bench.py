@@ -373,10 +373,11 @@ def run_gpu_arm(args):
     kernel_ms = statistics.mean(k_ms)
     # the timed region lasts only K x 0.4 ms; keep the same load running (untimed) until nvidia-smi has had ~0.6 s to
     # sample clocks / throttle reasons under it
-    # (a fixed count derived from the all-reduced step time, so every rank runs the same number of collective steps)
-    for _ in range(min(5000, int(600.0 / max(ms_per_step, 0.05)))):
-        step()
-    torch.cuda.synchronize()
+    # (single-GPU runs only: a long untimed queue of cross-rank barrier steps is not worth the risk at N > 1)
+    if world == 1:
+        for _ in range(min(5000, int(600.0 / max(ms_per_step, 0.05)))):
+            step()
+        torch.cuda.synchronize()
     exchange_ms = None
     if world > 1:  # cost of the label exchange alone (barrier or all-gather), CUDA events, same stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
