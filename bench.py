@@ -483,7 +483,27 @@ def run_gpu_arm(args):
             t0 = time.perf_counter()
             est_nd.predict(Xnd)
             nd_t.append(time.perf_counter() - t0)
+        c_port_info = {}
+        try:  # plain-C OpenMP restatement (oracle/linear_predict.c): what the host cores can do without Python in the way
+            from oracle import c_port
+
+            rows_c = X_host[: args.cpu_rows]
+            c_port.predict_indices(rows_c[:10_000], coef, intercept)
+            ct = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                idx_c = c_port.predict_indices(rows_c, coef, intercept)
+                ct.append(time.perf_counter() - t0)
+            c_port_info = {
+                "c_port_value": args.cpu_rows / min(ct),
+                "c_port_threads": c_port.num_threads(),
+                "c_port_note": "oracle/linear_predict.c, float64 scores over the fp32 rows, OpenMP over rows; labels "
+                + ("equal" if np.array_equal(idx_c, labels_host[: args.cpu_rows]) else "DIFFER from") + " the GPU's",
+            }
+        except Exception as exc:  # the C port is optional evidence, never a reason to lose the bench line
+            c_port_info = {"c_port_value": None, "c_port_note": f"unavailable: {exc!r}"}
         cpu_baseline = {
+            **c_port_info,
             "ndarray_value": args.cpu_rows / min(nd_t),
             "ndarray_note": "bare LogisticRegression.predict on a C-order float64 ndarray (no DataFrame, no list conversion)",
             "value": rps,

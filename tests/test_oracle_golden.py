@@ -177,3 +177,24 @@ def test_mlp_oracle_pinned_to_torch():
     assert omlp.canonical_predictor({"w1": w[0], "b1": w[1], "w2": w[2], "b2": w[3]}, pd.DataFrame(X[:5])) == [
         float(v) for v in want[:5]
     ]
+
+
+def test_c_restatement_matches_numpy_and_sklearn(digits_model, synthetic_digits, binary_mock):
+    """oracle/linear_predict.c (plain C, float64) against the numpy restatement, sklearn's labels and the fixtures."""
+    from oracle import c_port
+
+    c_port.build()
+    coef, intercept, classes = digits_model["coef"], digits_model["intercept"], digits_model["classes"]
+    X = synthetic_digits["X"]
+    for arr in (X.astype(np.float64), X.astype(np.float32)):
+        idx = c_port.predict_indices(arr, coef, intercept)
+        np.testing.assert_array_equal(classes[idx], synthetic_digits["labels_f64"])
+    big = np.random.default_rng(5).integers(0, 17, size=(200_000, 64)).astype(np.float64)
+    want = olin.predict_indices(olin.decision_function(big, coef, intercept))
+    np.testing.assert_array_equal(c_port.predict_indices(big, coef, intercept), want)
+    np.testing.assert_array_equal(_estimator(digits_model).predict(big[:5000]), classes[want[:5000]])
+    got = c_port.predict_indices(binary_mock["X"], binary_mock["coef"], binary_mock["intercept"])
+    np.testing.assert_array_equal(binary_mock["classes"][got], binary_mock["labels"])
+    ties = c_port.predict_indices(np.array([[2.0, 1.0], [1.0, 1.0]]), np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.zeros(3))
+    np.testing.assert_array_equal(ties, [0, 0])
+    assert c_port.num_threads() >= 1
