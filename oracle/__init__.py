@@ -14,7 +14,7 @@ Where the arithmetic lives: UnionML itself contains none.  The user predictor
 ``LinearClassifierMixin.predict`` (``sklearn/linear_model/_base.py:366-427``, scikit-learn is
 *unpinned* in ``/root/reference/requirements.txt:12``; 1.9.0 is installed in this image), which is
 ``X @ coef_.T + intercept_ -> argmax(axis=1) -> classes_.take``.  ``oracle.linear`` restates that
-published algorithm in numpy; ``oracle.unionml_path`` restates the UnionML wrapper around it
+published algorithm in numpy and ``oracle/linear_predict.c`` in plain C (``oracle.c_port`` loads it); ``oracle.unionml_path`` restates the UnionML wrapper around it
 (no flytekit); ``oracle.mlp`` restates the PyTorch quickstart predictor.
 
 Parity pinning (see ``tests/test_oracle_golden.py``): the restatement is checked against
