@@ -365,3 +365,60 @@ def test_cli_serve_sets_model_path_and_starts_uvicorn(monkeypatch, tmp_path):
     assert calls["app"] == "app:app" and calls["port"] == 8123
     with pytest.raises(SystemExit):
         cli.main(["serve", "app:app", "--model-path", str(tmp_path / "missing.joblib")])
+
+
+def test_predictor_host_checks_without_a_gpu():
+    """Validation that runs before the device is touched: fitted-ness, feature names, pipeline unwrapping."""
+    from sklearn.exceptions import NotFittedError
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+
+    from unionml_b200 import predictors as P
+
+    with pytest.raises(NotFittedError):
+        P._check_fitted(LogisticRegression())
+    frame = load_digits(as_frame=True).frame
+    X, y = frame[[c for c in frame if c != "target"]], frame["target"]
+    est = LogisticRegression(max_iter=200).fit(X.iloc[:300], y.iloc[:300])
+    P._check_fitted(est)
+    P._check_feature_names(est, X.iloc[:3])  # same names, same order: fine
+    with pytest.raises(ValueError, match="feature names"):
+        P._check_feature_names(est, X.iloc[:3, ::-1])
+    with pytest.raises(ValueError, match="feature names"):
+        P._check_feature_names(est, X.iloc[:3, :10])
+    P._check_feature_names(est, X.iloc[:3].to_numpy())  # ndarray: nothing to check, like sklearn
+
+    pipe = Pipeline([("scale", StandardScaler()), ("clf", LogisticRegression(max_iter=200))]).fit(X.iloc[:300], y.iloc[:300])
+    clf, shift, scale = P.unwrap_pipeline(pipe)
+    assert clf is pipe.named_steps["clf"]
+    np.testing.assert_array_equal(shift, pipe.named_steps["scale"].mean_)
+    np.testing.assert_allclose(scale, 1.0 / pipe.named_steps["scale"].scale_)
+    # folding (x - shift) * scale into W, b reproduces the pipeline's decision function
+    Xs = X.iloc[300:400].to_numpy()
+    folded_w = clf.coef_ * scale
+    folded_b = clf.intercept_ - folded_w @ shift
+    np.testing.assert_allclose(Xs @ folded_w.T + folded_b, pipe.decision_function(X.iloc[300:400]), rtol=1e-10, atol=1e-10)
+    assert P.unwrap_pipeline(est) == (est, None, None)
+    no_mean = Pipeline([("s", StandardScaler(with_mean=False)), ("c", LogisticRegression(max_iter=50))]).fit(X.iloc[:200], y.iloc[:200])
+    _, shift2, scale2 = P.unwrap_pipeline(no_mean)
+    assert shift2 is None and scale2 is not None
+    with pytest.raises(TypeError, match="StandardScaler"):
+        P.unwrap_pipeline(Pipeline([("m", MinMaxScaler()), ("c", LogisticRegression())]))
+
+
+def test_mlp_layer_extraction():
+    import torch.nn as nn
+
+    from unionml_b200.predictors import _mlp_layers
+
+    class Net(nn.Module):  # the reference's PytorchModel layout (quickstart.py:14-24)
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
+
+    l1, l2 = _mlp_layers(Net())
+    assert l1.weight.shape == (32, 64) and l2.weight.shape == (10, 32)
+    with pytest.raises(TypeError, match="Linear -> ReLU -> Linear"):
+        _mlp_layers(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2)))
+    with pytest.raises(TypeError):
+        _mlp_layers(nn.Linear(4, 2))

@@ -57,13 +57,44 @@ def _check_feature_names(estimator, features) -> None:
         )
 
 
+def unwrap_pipeline(estimator):
+    """``Pipeline(StandardScaler, <linear classifier>)`` (the MNIST tutorial's model, ``docs/tutorials/mnist.md:116-124``)
+    -> ``(classifier, shift, scale)`` with ``x' = (x - shift) * scale``; a bare classifier -> ``(classifier, None, None)``.
+
+    Only that two-step shape is folded into the device model; any other pipeline raises ``TypeError`` (run its
+    transformers in a ``@dataset.feature_transformer`` instead).
+    """
+    steps = getattr(estimator, "steps", None)
+    if steps is None:
+        return estimator, None, None
+    from sklearn.preprocessing import StandardScaler
+
+    if len(steps) != 2 or not isinstance(steps[0][1], StandardScaler):
+        raise TypeError(
+            "linear_argmax folds Pipeline(StandardScaler, linear classifier) only; found steps "
+            f"{[type(s).__name__ for _, s in steps]}"
+        )
+    scaler, clf = steps[0][1], steps[1][1]
+    if not hasattr(scaler, "n_features_in_"):
+        _check_fitted(object())  # raises NotFittedError with sklearn's wording
+    shift = getattr(scaler, "mean_", None) if getattr(scaler, "with_mean", True) else None
+    scale_ = getattr(scaler, "scale_", None) if getattr(scaler, "with_std", True) else None
+    scale = None if scale_ is None else 1.0 / np.asarray(scale_, dtype=np.float64)
+    return clf, (None if shift is None else np.asarray(shift, dtype=np.float64)), scale
+
+
 def device_model(estimator, engine: Engine | None = None) -> LinearModel:
-    """The estimator's ``coef_``/``intercept_`` staged on the device, cached per estimator object and weights."""
-    _check_fitted(estimator)
+    """The estimator's ``coef_``/``intercept_`` (with a leading StandardScaler folded in) staged on the device, cached
+    per estimator object and weights."""
+    clf, shift, scale = unwrap_pipeline(estimator)
+    _check_fitted(clf)
     engine = engine or get_engine()
-    coef = np.asarray(estimator.coef_)
-    intercept = np.asarray(estimator.intercept_)
-    key = (id(engine), coef.shape, coef.dtype.str, hash(coef.tobytes()), hash(intercept.tobytes()))
+    coef = np.asarray(clf.coef_)
+    intercept = np.asarray(clf.intercept_)
+    key = (
+        id(engine), coef.shape, coef.dtype.str, hash(coef.tobytes()), hash(intercept.tobytes()),
+        None if shift is None else hash(shift.tobytes()), None if scale is None else hash(scale.tobytes()),
+    )
     with _cache_lock:
         try:
             hit = _model_cache.get(estimator)
@@ -71,7 +102,9 @@ def device_model(estimator, engine: Engine | None = None) -> LinearModel:
             hit = None
         if hit is not None and hit[0] == key:
             return hit[1]
-        dm = engine.load_linear(coef, intercept, getattr(estimator, "classes_", None))
+        dm = engine.load_linear(coef, intercept, getattr(clf, "classes_", None))
+        if shift is not None or scale is not None:
+            dm.set_affine(shift=shift, scale=scale)
         try:
             _model_cache[estimator] = (key, dm)
         except TypeError:
@@ -85,7 +118,7 @@ def linear_predict_labels(estimator, features, exact: bool | None = None, engine
     dm = device_model(estimator, engine)
     _check_feature_names(estimator, features)
     idx, _stats = engine.predict_host(dm, features, exact=_exact_default() if exact is None else exact)
-    classes = getattr(estimator, "classes_", None)
+    classes = getattr(estimator, "classes_", None)  # a Pipeline forwards classes_ of its final step
     if classes is None:
         return idx.astype(np.int64)
     return np.asarray(classes).take(idx, axis=0)
