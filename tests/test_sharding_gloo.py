@@ -56,3 +56,52 @@ def test_gather_labels_world2_gloo(tmp_path, n_rows):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_rows, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# predict_sharded end to end on CPU: the engine is replaced by a stub that writes the oracle's labels through the raw
+# pointer it is handed (exactly how the CUDA library is driven), the exchange is a real gloo all-gather
+# ---------------------------------------------------------------------------------------------------------------
+class _StubEngine:
+    device = 0
+
+    def __init__(self, labels_for_shard):
+        self._labels = labels_for_shard
+        self.calls = []
+
+    def predict(self, model, batch, exact=True, out_device_ptr=None, want_stats=True):
+        import ctypes
+
+        src = np.ascontiguousarray(self._labels, dtype=np.int32)
+        ctypes.memmove(out_device_ptr, src.ctypes.data, src.nbytes)
+        self.calls.append((exact, src.size))
+        return None, None
+
+
+def _sharded_worker(rank, world, port, n_rows, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import linear as olin
+        from unionml_b200.sharding import predict_sharded
+
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", "digits_lr.npz"))
+        X = np.random.default_rng(77).integers(0, 17, size=(n_rows, 64)).astype(np.float64)
+        full = olin.predict_indices(olin.decision_function(X, z["coef"], z["intercept"])).astype(np.int32)
+        lo, hi = shard_bounds(n_rows, rank, world)
+        counts = shard_counts(n_rows, world)
+        eng = _StubEngine(full[lo:hi])
+        labels_all = torch.full((n_rows,), -1, dtype=torch.int32)
+        got = predict_sharded(eng, model=None, batch=None, row_offset=lo, counts=counts, exact=True, labels_all=labels_all)
+        np.testing.assert_array_equal(got.numpy(), full)
+        assert eng.calls == [(True, hi - lo)]
+        open(os.path.join(out_dir, f"sharded_ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [2048, 2051])
+def test_predict_sharded_world2_gloo_with_stub_engine(tmp_path, n_rows):
+    world = 2
+    mp.spawn(_sharded_worker, args=(world, _free_port(), n_rows, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"sharded_ok{r}").exists() for r in range(world))
