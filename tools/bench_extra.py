@@ -82,9 +82,10 @@ def main():
                      "achieved_GBs": args.rows_mlp * 256 / (mean_ms * 1e-3) / 1e9,
                      "fp32_TFLOPs": args.rows_mlp * 4736 / (mean_ms * 1e-3) / 1e12}
     _, st = eng.predict_mlp(mlp, bm, exact=True, out_device_ptr=out.data_ptr())
-    from oracle import mlp as omlp  # checker only
-
-    want = omlp.predict_indices_f64(Xh[:1_000_000], z["w1"], z["b1"], z["w2"], z["b2"])
+    # parity spot check in float64 numpy (tools/ may not touch oracle/): argmax of W2 relu(W1 x + b1) + b2
+    x64 = Xh[:1_000_000].astype(np.float64)
+    hid = np.maximum(x64 @ z["w1"].astype(np.float64).T + z["b1"].astype(np.float64), 0.0)
+    want = (hid @ z["w2"].astype(np.float64).T + z["b2"].astype(np.float64)).argmax(1)
     ok = bool(np.array_equal(out[:1_000_000].cpu().numpy(), want))
     print(json.dumps({"config": "cfg5 MLP 64->32->10", "rows": args.rows_mlp, **res, "rows_rescored_fp64": st["n_flagged"],
                       "roofline_frac_of_measured_hbm": res["exact"]["achieved_GBs"] / PEAK,
