@@ -333,7 +333,7 @@ def run_gpu_arm(args):
     how = "one NVLS multicast store per tile" if (exchange is not None and exchange.multicast) else "one store per peer per tile"
     args.gather_used = {"push": f"kernel stores {args.wire} labels locally, thin copy kernel pushes the slice ({how.replace(' per tile', '')}) + barrier",
                         "fused": f"fused label stores ({args.wire}, {how}) from the kernel epilogue over NVLink (symmetric memory) + barrier",
-                        "nccl": "ncclAllGather of int32 labels", "none": "none"}[gather]
+                        "nccl": f"ncclAllGather of {args.wire} labels", "none": "none"}[gather]
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
