@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define UML_B200_ABI_VERSION 1
+#define UML_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define UML_API __attribute__((visibility("default")))
@@ -73,7 +73,8 @@ typedef struct uml_stats {
   int64_t h2d_bytes;
   int64_t d2h_bytes;
   int32_t kernel_launches; /* kernels of this library launched by the call                                            */
-  int32_t path;            /* 1 = TMA fp32 tile kernel, 2 = generic fp64 kernel, 3 = MLP kernel                        */
+  int32_t path;            /* 1 = TMA fp32 tile kernel, 2 = generic fp64 kernel, 3 = MLP kernel, 4 = small-batch fp64
+                              kernel of the online path (<= 64 rows, one CUDA graph: H2D, kernel, D2H)                 */
 } uml_stats;
 
 typedef struct uml_device_info {
@@ -152,10 +153,26 @@ UML_API int uml_labels_count_equal(uml_engine* e, const void* labels_dev, int la
 UML_API int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst, int64_t bytes);
 /* end to end from HOST rows to HOST labels in one call (the /predict and Model.predict(features=...) shape): chunked
  * H2D, staging kernel, scoring kernel and label D2H pipelined on two streams; never holds more than a few chunks in
- * HBM.  host_ptr/labels_out may be pageable or pinned (uml_host_alloc). */
+ * HBM.  host_ptr/labels_out may be pageable or pinned (uml_host_alloc); large pageable sources are gathered into pinned
+ * bounce buffers by a few host threads.  In exact mode rows inside the fp32 error bound are re-scored in float64 from
+ * the caller's own values (float64 / int64 / int32 features that do not survive the fp32 down-cast included).  Batches
+ * of <= 64 rows (the /predict shape, fastapi.py:50-64) take a one-kernel float64 route replayed as a CUDA graph. */
 UML_API int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
                             int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
                             int mode, int64_t chunk_rows, uml_stats* stats);
+
+/* the same call returning `classes_[idx]` as float64 per row (sklearn/linear_model/_base.py:423 + the float conversion
+ * of the canonical predictor, README.md:92) - the take runs on the device per chunk and the values travel back instead
+ * of the indices.  classes_host: n_classes float64 values (a binary model passes its 2 classes). */
+UML_API int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
+                                   int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                   const double* classes_host, int n_classes, double* values_out, int mode,
+                                   int64_t chunk_rows, uml_stats* stats);
+/* class probabilities of a resident batch: LogisticRegression.predict_proba (sklearn/linear_model/_logistic.py) =
+ * softmax of decision_function (sigmoid for the binary layout: columns [1 - p, p]).  fp32 scores and exp;
+ * proba_out: n_rows x n_classes row-major fp32 (n_classes = 2 for a binary model), host or device memory. */
+UML_API int uml_linear_predict_proba(uml_engine* e, const uml_model* m, const uml_batch* b, float* proba_out,
+                             int proba_on_device);
 
 /* ---- 2-layer MLP predictor (tests/integration/pytorch_app/quickstart.py:14-24,68-70) -------------------------- */
 /* w1: hidden x in, b1: hidden, w2: out x hidden, b2: out (torch nn.Linear layout, fp32).  Labels = argmax of

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     missing = [s for s in _declared_symbols() if not hasattr(handle, s)]
     assert not missing, missing
     handle.uml_abi_version.restype = ctypes.c_int
-    assert handle.uml_abi_version() == 1
+    assert handle.uml_abi_version() == 2
 
 
 def test_python_binding_covers_the_header(built_lib):

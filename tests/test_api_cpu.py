@@ -265,8 +265,9 @@ def test_digits_app_known_answers(digits_app, digits_model):
     # the app trains the very model stored in tests/golden/digits_lr.npz
     np.testing.assert_allclose(model.artifact.model_object.coef_, digits_model["coef"], rtol=0, atol=1e-12)
     assert model.artifact.metrics["train"] == 1.0 and abs(model.artifact.metrics["test"] - 0.9639) < 1e-3
-    # reader path (ref. model.py:473-495): predictions for the whole frame
-    assert len(model.predict()) == 0 if False else True
+    # no features and a reader without arguments: the reference refuses (model.py:727-728) - so does the mirror
+    with pytest.raises(ValueError, match="At least one of features"):
+        model.predict()
 
 
 def test_fastapi_predict_and_health(digits_app, tmp_path, monkeypatch):

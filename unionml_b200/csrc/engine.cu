@@ -1,12 +1,26 @@
 // C ABI of the uml_b200 engine (see include/uml_b200.h): device binding, model/batch residency, predict calls.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "uml_common.cuh"
+
+// NVTX ranges around the phases of a call (stage / score / re-score / exchange); free when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 namespace uml {
 cudaError_t launch_finite_scan(const float* x, int64_t ld, int64_t rows, int n_features, StageResult* result,
@@ -31,11 +45,102 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 static thread_local std::string g_create_error;
 
+constexpr int kSmallRows = 64;              // online path: batches up to this many rows take the one-kernel fp64 route
+constexpr int64_t kSmallBytes = 256 << 10;   // ... when their raw feature block fits the pinned request buffer
+
 struct HostMirror {  // pinned; device counters are copied here
   int flag_count;
   int pad;
   unsigned long long counters[4];
   StageResult stage;
+  uml::SmallResult small[kSmallRows];
+};
+
+// Host threads that gather a pageable source chunk into a pinned bounce buffer: cudaMemcpy from pageable memory is
+// staged by the driver on one thread; a few threads doing plain memcpy into page-locked memory keep the link busy.
+class CopyPool {
+ public:
+  struct Task {  // `rows` runs of n bytes (rows == 1: one contiguous run)
+    char* dst;
+    const char* src;
+    size_t n;
+    size_t rows = 1, dpitch = 0, spitch = 0;
+  };
+  explicit CopyPool(int n_threads) {
+    for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  // copy every task; the calling thread works too and returns when all are done
+  void run(const std::vector<Task>& tasks) {
+    if (tasks.empty()) return;
+    auto job = std::make_shared<Job>();
+    job->tasks = tasks.data();
+    job->n = tasks.size();
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      job_ = job;
+      ++generation_;
+    }
+    cv_work_.notify_all();
+    work(*job);
+    std::unique_lock<std::mutex> g(mu_);
+    cv_done_.wait(g, [&] { return job->done.load() == job->n; });
+    job_.reset();
+  }
+
+ private:
+  // a job owns its counters, so a worker that wakes up late only ever sees an exhausted index range of an old job
+  struct Job {
+    const Task* tasks = nullptr;
+    size_t n = 0;
+    std::atomic<size_t> next{0}, done{0};
+  };
+  void work(Job& job) {
+    for (;;) {
+      const size_t i = job.next.fetch_add(1);
+      if (i >= job.n) return;
+      const Task& t = job.tasks[i];
+      for (size_t r = 0; r < t.rows; ++r) memcpy(t.dst + r * t.dpitch, t.src + r * t.spitch, t.n);
+      if (job.done.fetch_add(1) + 1 == job.n) {
+        std::lock_guard<std::mutex> g(mu_);
+        cv_done_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_work_.wait(g, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+        job = job_;
+      }
+      if (job) work(*job);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::shared_ptr<Job> job_;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
+
+struct SmallGraph {  // one captured H2D -> linear_small_kernel -> D2H per (model, rows, features, dtype)
+  uint64_t model_uid = 0;
+  int n_rows = 0, n_features = 0, dtype = 0;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t last_use = 0;
 };
 
 struct uml_engine {
@@ -58,11 +163,28 @@ struct uml_engine {
   int64_t chunk_cap = 0;
   float* d_xchunk[3] = {nullptr, nullptr, nullptr};  // converted fp32 chunks (predict_host)
   int64_t xchunk_cap = 0;
+  double* d_vchunk[3] = {nullptr, nullptr, nullptr};  // class values of a chunk (predict_host_values)
+  int64_t vchunk_cap = 0;
+  double* d_classes = nullptr;
+  int classes_cap = 0;
+  void* h_bounce[3] = {nullptr, nullptr, nullptr};  // pinned bounce buffers for pageable sources
+  int64_t bounce_cap = 0;
+  CopyPool* pool = nullptr;
+  // online path (B <= kSmallRows): pinned request buffer, its device twin, result slots, cached graphs
+  void* h_req = nullptr;
+  void* d_req = nullptr;
+  uml::SmallResult* d_small = nullptr;
+  std::vector<SmallGraph> small_graphs;
+  uint64_t small_tick = 0;
+  bool small_graph_ok = true;
   HostMirror* h = nullptr;
 };
 
+static std::atomic<uint64_t> g_model_uid{1};
+
 struct uml_model {
   uml_engine* e = nullptr;
+  uint64_t uid = 0;  // changes whenever the device operands are re-uploaded (keys the cached small-batch graphs)
   LinearDeviceModel dm{};
   int n_features_in = 0;
   int n_classes_in = 0;  // as passed by the caller (1 for sklearn's binary layout)
@@ -183,6 +305,9 @@ int uml_engine_create(uml_engine** out, int device_id) {
   if ((err = cudaHostAlloc((void**)&e->h, sizeof(HostMirror), cudaHostAllocDefault)) != cudaSuccess)
     return fail("cudaHostAlloc", err);
   memset(e->h, 0, sizeof(HostMirror));
+  // the scoring steps do not memset these: the re-score kernel hands the flag list back empty (linear_kernels.cu)
+  if ((err = cudaMemset(e->d_flag_count, 0, sizeof(int))) != cudaSuccess) return fail("cudaMemset", err);
+  if ((err = cudaMemset(e->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", err);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -203,6 +328,16 @@ void uml_engine_destroy(uml_engine* e) {
   cudaFree(e->d_labels);
   for (auto p : e->d_chunk) cudaFree(p);
   for (auto p : e->d_xchunk) cudaFree(p);
+  for (auto p : e->d_vchunk) cudaFree(p);
+  cudaFree(e->d_classes);
+  for (auto p : e->h_bounce)
+    if (p) cudaFreeHost(p);
+  delete e->pool;
+  for (auto& g : e->small_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->h_req) cudaFreeHost(e->h_req);
+  cudaFree(e->d_req);
+  cudaFree(e->d_small);
   if (e->h) cudaFreeHost(e->h);
   for (auto ev : e->ev)
     if (ev) cudaEventDestroy(ev);
@@ -302,6 +437,7 @@ static int upload_model(uml_engine* e, uml_model* m, const std::vector<double>& 
   m->dm.b64 = m->d_b64;
   m->dm.cp = cp;
   m->dm.f_pad = f_pad;
+  m->uid = g_model_uid.fetch_add(1);
   return UML_OK;
 }
 
@@ -481,7 +617,8 @@ int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t
   const int F = n_features;
   const int64_t ld = (F + 3) / 4 * 4;
   const bool check = !(flags & UML_STAGE_SKIP_FINITE_CHECK);
-  const bool want64 = (flags & UML_STAGE_KEEP_F64) && (src_dtype == UML_F64 || src_dtype == UML_I64);
+  // float64 / int64 / int32 values may not survive the fp32 down-cast (|int32| > 2^24 does not)
+  const bool want64 = (flags & UML_STAGE_KEEP_F64) && (src_dtype == UML_F64 || src_dtype == UML_I64 || src_dtype == UML_I32);
 
   uml_batch* b = new uml_batch();
   b->e = e;
@@ -620,7 +757,7 @@ static int enqueue_predict(uml_engine* e, const uml_model* m, const LinearLaunch
   const bool tma = map != nullptr && uml::linear_tma_supported(m->dm, &why);
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[1], e->stream));
   if (tma) {
-    if (exact) UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+    NvtxRange r_score("uml:score");
     std::string err;
     cudaError_t ce = uml::launch_linear_tma(*map, m->dm, l, exact, fl, e->info.sm_count, e->stream, &err);
     if (ce != cudaSuccess) UML_FAIL(e, UML_ERR_CUDA, "linear_argmax_tma launch: %s %s", cudaGetErrorString(ce), err.c_str());
@@ -628,11 +765,13 @@ static int enqueue_predict(uml_engine* e, const uml_model* m, const LinearLaunch
     *path = 1;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
     if (exact) {
+      NvtxRange r_rescore("uml:rescore_f64");
       UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, false, e->info.sm_count, e->stream));
       *launches += 1;
     }
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[3], e->stream));
   } else {
+    NvtxRange r_score("uml:score_f64_generic");
     UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, true, e->info.sm_count, e->stream));
     *launches += 1;
     *path = 2;
@@ -708,8 +847,12 @@ static int predict_common(uml_engine* e, const uml_model* m, const uml_batch* b,
     d_labels = e->d_labels;
   }
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], e->stream));
-  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
-  UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  if (stats || !labels_on_device) {
+    // synchronous call: the counters are read back at the end, start them from zero.  The asynchronous step (device
+    // labels, no stats) needs no memset at all: the flag list is handed back empty by the previous re-score kernel.
+    UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  }
   LinearLaunch l{};
   l.x = b->x;
   l.x64 = b->x64;
@@ -827,11 +970,152 @@ int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst,
   return UML_OK;
 }
 
-int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
-                            int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
-                            int mode, int64_t chunk_rows, uml_stats* stats) {
-  if (!e || !m || (!host_ptr && n_rows > 0) || (!labels_out && n_rows > 0) || n_rows < 0 || n_features < 1)
+// ---------------------------------------------------------------------------------------------------------------
+// host rows -> host labels
+// ---------------------------------------------------------------------------------------------------------------
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static bool lossy_capable(int dtype) { return dtype == UML_F64 || dtype == UML_I64 || dtype == UML_I32; }
+
+// gather tasks for rows [r0, r0+rows) of the host source into a compact chunk (row-major [rows][F] or feature-major
+// [F][rows]) at `dst`; contiguous runs are cut into <= 1 MiB pieces so the pool's threads share them
+static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, const void* host, const SrcLayout& L,
+                               int64_t r0, int64_t rows, int F) {
+  tasks.clear();
+  const char* src = (const char*)host;
+  const size_t piece = 1u << 20;
+  auto add_run = [&](char* d, const char* s_, size_t n) {
+    for (size_t o = 0; o < n; o += piece) tasks.push_back({d + o, s_ + o, std::min(piece, n - o)});
+  };
+  if (!L.feature_major) {
+    const size_t width = (size_t)F * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
+    if (spitch == width) {
+      add_run(dst, src + (size_t)r0 * spitch, width * (size_t)rows);
+    } else {
+      // strided rows (a column slice of a wider C-order array): blocks of rows, each row its own run
+      const int64_t rows_per_task = std::max<int64_t>(1, (int64_t)(piece / width));
+      for (int64_t r = 0; r < rows; r += rows_per_task) {
+        const int64_t n = std::min(rows_per_task, rows - r);
+        tasks.push_back({dst + (size_t)r * width, src + (size_t)(r0 + r) * spitch, width, (size_t)n, width, spitch});
+      }
+    }
+  } else {
+    const size_t run = (size_t)rows * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
+    for (int f = 0; f < F; ++f) add_run(dst + (size_t)f * run, src + (size_t)f * spitch + (size_t)r0 * L.elem, run);
+  }
+}
+
+// B <= kSmallRows: request block -> pinned buffer -> (graph: H2D, linear_small_kernel, D2H) -> labels.  fp64 from the
+// caller's own values, so the result is the exact-mode result for either mode.
+static int predict_host_small(uml_engine* e, const uml_model* m, const void* host_ptr, int n_rows, int F,
+                              const SrcLayout& L, int src_dtype, int32_t* labels_out, double* values_out,
+                              const double* classes, int n_classes, uml_stats* stats) {
+  NvtxRange r_all("uml:predict_host_small");
+  const size_t width = (size_t)F * L.elem;
+  const size_t bytes = width * (size_t)n_rows;
+  if (!e->h_req) {
+    UML_CUDA(e, cudaHostAlloc(&e->h_req, (size_t)kSmallBytes, cudaHostAllocDefault));
+    UML_CUDA(e, cudaMalloc(&e->d_req, (size_t)kSmallBytes));
+    UML_CUDA(e, cudaMalloc((void**)&e->d_small, sizeof(uml::SmallResult) * kSmallRows));
+  }
+  // gather into the pinned request buffer as compact row-major rows (the kernel reads any order, but a compact
+  // block keeps the H2D copy one contiguous piece)
+  {
+    const char* src = (const char*)host_ptr;
+    char* dst = (char*)e->h_req;
+    if (!L.feature_major) {
+      const size_t spitch = (size_t)L.pitch_elems * L.elem;
+      if (spitch == width) memcpy(dst, src, bytes);
+      else for (int r = 0; r < n_rows; ++r) memcpy(dst + (size_t)r * width, src + (size_t)r * spitch, width);
+    } else {
+      const size_t spitch = (size_t)L.pitch_elems * L.elem;
+      for (int f = 0; f < F; ++f)
+        for (int r = 0; r < n_rows; ++r)
+          memcpy(dst + (size_t)r * width + (size_t)f * L.elem, src + (size_t)f * spitch + (size_t)r * L.elem, L.elem);
+    }
+  }
+  uml::SrcView view{e->d_req, src_dtype, (long long)F, 1};
+  auto enqueue = [&](cudaStream_t s) -> cudaError_t {
+    cudaError_t ce;
+    if ((ce = cudaMemcpyAsync(e->d_req, e->h_req, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return ce;
+    if ((ce = uml::launch_linear_small(m->dm, view, n_rows, e->d_small, s)) != cudaSuccess) return ce;
+    return cudaMemcpyAsync(e->h->small, e->d_small, sizeof(uml::SmallResult) * (size_t)n_rows, cudaMemcpyDeviceToHost, s);
+  };
+  static const bool no_graph = getenv("UML_B200_NO_GRAPH") != nullptr;
+  bool launched = false;
+  if (e->small_graph_ok && !no_graph) {
+    SmallGraph* hit = nullptr;
+    for (auto& g : e->small_graphs)
+      if (g.model_uid == m->uid && g.n_rows == n_rows && g.n_features == F && g.dtype == src_dtype) hit = &g;
+    if (!hit) {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        cudaError_t body = enqueue(e->stream);
+        ce = cudaStreamEndCapture(e->stream, &graph);
+        if (body != cudaSuccess) ce = body;
+      }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        (void)cudaGetLastError();
+        e->small_graph_ok = false;  // capture is not available here (e.g. the caller's stream is itself capturing)
+      } else {
+        if (e->small_graphs.size() >= 16) {  // evict the least recently used
+          size_t lru = 0;
+          for (size_t i = 1; i < e->small_graphs.size(); ++i)
+            if (e->small_graphs[i].last_use < e->small_graphs[lru].last_use) lru = i;
+          cudaGraphExecDestroy(e->small_graphs[lru].exec);
+          e->small_graphs.erase(e->small_graphs.begin() + (long)lru);
+        }
+        e->small_graphs.push_back({m->uid, n_rows, F, src_dtype, exec, 0});
+        hit = &e->small_graphs.back();
+      }
+    }
+    if (hit) {
+      hit->last_use = ++e->small_tick;
+      UML_CUDA(e, cudaGraphLaunch(hit->exec, e->stream));
+      launched = true;
+    }
+  }
+  if (!launched) UML_CUDA(e, enqueue(e->stream));
+  UML_CUDA(e, cudaStreamSynchronize(e->stream));
+  int64_t n_bad = 0, n_amb = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const uml::SmallResult& q = e->h->small[r];
+    if (labels_out) labels_out[r] = q.label;
+    if (values_out) values_out[r] = (q.label >= 0 && q.label < n_classes) ? classes[q.label] : NAN;
+    n_bad += q.status & 1;
+    n_amb += (q.status >> 1) & 1;
+  }
+  if (stats) {
+    stats->n_rows = n_rows;
+    stats->n_nonfinite = n_bad;
+    stats->n_ambiguous = n_amb;
+    stats->kernel_launches = 1;
+    stats->path = 4;
+    stats->h2d_bytes = (int64_t)bytes;
+    stats->d2h_bytes = (int64_t)sizeof(uml::SmallResult) * n_rows;
+  }
+  if (n_bad > 0) UML_FAIL(e, UML_ERR_NONFINITE, "Input X contains NaN or infinity.");
+  return UML_OK;
+}
+
+static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
+                             int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                             double* values_out, const double* classes, int n_classes, int mode, int64_t chunk_rows,
+                             uml_stats* stats) {
+  if (!e || !m || (!host_ptr && n_rows > 0) || (!labels_out && !values_out && n_rows > 0) || n_rows < 0 || n_features < 1)
     return UML_ERR_INVALID;
+  if (values_out && (!classes || n_classes < 1)) return UML_ERR_INVALID;
   if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
   if (n_features != m->n_features_in)
     UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.", n_features,
@@ -844,12 +1128,18 @@ int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_
   int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
   if (rc != UML_OK) return rc;
   const int F = n_features;
+  if (n_rows <= kSmallRows && (int64_t)F * L.elem * n_rows <= kSmallBytes)
+    return predict_host_small(e, m, host_ptr, (int)n_rows, F, L, src_dtype, labels_out, values_out, classes, n_classes, stats);
+
+  NvtxRange r_all("uml:predict_host");
   const int64_t ld = (F + 3) / 4 * 4;
   const bool exact = mode == UML_PREDICT_EXACT;
   const int64_t row_bytes = (int64_t)F * L.elem;
-  if (chunk_rows <= 0) chunk_rows = std::max<int64_t>(4096, (32ll << 20) / (ld * 4));
+  if (chunk_rows <= 0) chunk_rows = std::max<int64_t>(4096, (32ll << 20) / std::max<int64_t>(ld * 4, row_bytes));
   chunk_rows = std::min<int64_t>((chunk_rows + 127) / 128 * 128, (n_rows + 127) / 128 * 128);
   const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld;
+  // pageable sources of any size worth the trouble go through pinned bounce buffers filled by the copy pool
+  const bool bounce = n_rows * row_bytes >= (8ll << 20) && !host_ptr_is_pinned(host_ptr) && !getenv("UML_B200_NO_BOUNCE");
 
   if (!direct && (rc = ensure_chunks(e, chunk_rows * row_bytes)) != UML_OK) return rc;
   if (e->xchunk_cap < chunk_rows * ld) {
@@ -861,41 +1151,112 @@ int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_
     for (auto& p : e->d_xchunk) UML_CUDA(e, cudaMalloc((void**)&p, (size_t)chunk_rows * ld * 4));
     e->xchunk_cap = chunk_rows * ld;
   }
+  // bytes of one row as it travels: `direct` rows keep their padding up to ld
+  const int64_t wire_row_bytes = direct ? ld * 4 : row_bytes;
+  if (bounce) {
+    if (e->bounce_cap < chunk_rows * wire_row_bytes) {
+      for (auto& p : e->h_bounce) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+      }
+      e->bounce_cap = 0;
+      for (auto& p : e->h_bounce) UML_CUDA(e, cudaHostAlloc(&p, (size_t)(chunk_rows * wire_row_bytes), cudaHostAllocDefault));
+      e->bounce_cap = chunk_rows * wire_row_bytes;
+    }
+    if (!e->pool) {
+      int n = 0;
+      if (const char* env = getenv("UML_B200_COPY_THREADS")) n = atoi(env);
+      if (n <= 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, std::thread::hardware_concurrency() / 4u));
+      e->pool = new CopyPool(n - 1);  // the calling thread is the n-th worker
+    }
+  }
+  if (values_out) {
+    if (e->vchunk_cap < chunk_rows) {
+      for (auto& p : e->d_vchunk) {
+        cudaFree(p);
+        p = nullptr;
+      }
+      e->vchunk_cap = 0;
+      for (auto& p : e->d_vchunk) UML_CUDA(e, cudaMalloc((void**)&p, (size_t)chunk_rows * 8));
+      e->vchunk_cap = chunk_rows;
+    }
+    if (e->classes_cap < n_classes) {
+      cudaFree(e->d_classes);
+      e->d_classes = nullptr;
+      e->classes_cap = 0;
+      UML_CUDA(e, cudaMalloc((void**)&e->d_classes, (size_t)n_classes * 8));
+      e->classes_cap = n_classes;
+    }
+  }
   if ((rc = ensure_labels(e, 3 * chunk_rows)) != UML_OK) return rc;
   if (exact && (rc = ensure_flags(e, chunk_rows)) != UML_OK) return rc;
 
   const bool timed = stats != nullptr;
   cudaStream_t cs = e->stream;
-  if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], cs));
-  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), cs));
-  UML_CUDA(e, cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), cs));
-  UML_CUDA(e, cudaEventRecord(e->chunk_ev[6], cs));
-  UML_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[6], 0));
+  // errors inside the pipeline: both streams must be idle before returning - async copies still reference the
+  // caller's host_ptr / labels_out
+#define HOST_CUDA(CALL)                                                          \
+  do {                                                                           \
+    cudaError_t _e3 = (CALL);                                                    \
+    if (_e3 != cudaSuccess) {                                                    \
+      cudaStreamSynchronize(cs);                                                 \
+      cudaStreamSynchronize(e->copy_stream);                                     \
+      UML_FAIL(e, _e3 == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA, "%s failed: %s", #CALL, \
+               cudaGetErrorString(_e3));                                         \
+    }                                                                            \
+  } while (0)
+  if (timed) HOST_CUDA(cudaEventRecord(e->ev[0], cs));
+  HOST_CUDA(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), cs));
+  HOST_CUDA(cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), cs));
+  HOST_CUDA(cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), cs));
+  if (values_out) HOST_CUDA(cudaMemcpyAsync(e->d_classes, classes, (size_t)n_classes * 8, cudaMemcpyHostToDevice, cs));
+  HOST_CUDA(cudaEventRecord(e->chunk_ev[6], cs));
+  HOST_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[6], 0));
   int launches = 0, path = 0;
   int64_t h2d = 0, d2h = 0;
   bool used[3] = {false, false, false};
   int slot = 0;
+  std::vector<CopyPool::Task> tasks;
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
     const int64_t rows = std::min(chunk_rows, n_rows - r0);
     float* xc = e->d_xchunk[slot];
-    // (1) H2D on the copy stream, once the previous user of this slot has finished scoring
-    if (used[slot]) UML_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));
-    if (direct) {
-      UML_CUDA(e, cudaMemcpyAsync(xc, (const char*)host_ptr + (size_t)r0 * ld * 4, (size_t)rows * ld * 4,
+    void* raw = direct ? (void*)xc : e->d_chunk[slot];
+    // (1) H2D on the copy stream, once the previous user of this slot has finished scoring (the re-score reads the
+    //     raw chunk, so that includes it)
+    if (used[slot]) HOST_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));
+    {
+      NvtxRange r_h2d("uml:h2d");
+      if (bounce) {
+        if (used[slot]) HOST_CUDA(cudaEventSynchronize(e->chunk_ev[slot]));  // the slot's previous H2D has left the bounce buffer
+        if (direct) {  // already the resident layout (padding included): one contiguous run
+          tasks.clear();
+          const char* src0 = (const char*)host_ptr + (size_t)r0 * ld * 4;
+          const size_t total = (size_t)rows * ld * 4, piece = 1u << 20;
+          for (size_t o = 0; o < total; o += piece)
+            tasks.push_back({(char*)e->h_bounce[slot] + o, src0 + o, std::min(piece, total - o)});
+        } else {
+          build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F);
+        }
+        e->pool->run(tasks);
+        HOST_CUDA(cudaMemcpyAsync(raw, e->h_bounce[slot], (size_t)(rows * wire_row_bytes), cudaMemcpyHostToDevice, e->copy_stream));
+      } else if (direct) {
+        HOST_CUDA(cudaMemcpyAsync(xc, (const char*)host_ptr + (size_t)r0 * ld * 4, (size_t)rows * ld * 4,
                                   cudaMemcpyHostToDevice, e->copy_stream));
-    } else {
-      UML_CUDA(e, copy_chunk_h2d(e->d_chunk[slot], host_ptr, L, r0, rows, F, e->copy_stream));
+      } else {
+        HOST_CUDA(copy_chunk_h2d(raw, host_ptr, L, r0, rows, F, e->copy_stream));
+      }
     }
-    h2d += rows * row_bytes;
-    UML_CUDA(e, cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
-    UML_CUDA(e, cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
+    h2d += rows * wire_row_bytes;
+    HOST_CUDA(cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
+    HOST_CUDA(cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
     // (2) transpose / down-cast (+ finiteness) on the compute stream
     if (!direct) {
-      UML_CUDA(e, uml::launch_stage_convert(e->d_chunk[slot], src_dtype, L.feature_major, L.feature_major ? rows : F,
-                                            rows, F, xc, ld, nullptr, 0, e->d_stage, true, cs));
+      NvtxRange r_stage("uml:stage_convert");
+      HOST_CUDA(uml::launch_stage_convert(raw, src_dtype, L.feature_major, L.feature_major ? rows : F, rows, F, xc, ld,
+                                          nullptr, 0, e->d_stage, true, cs));
       launches += 1;
     } else if (!exact) {
-      UML_CUDA(e, uml::launch_finite_scan(xc, ld, rows, F, e->d_stage, cs));
+      HOST_CUDA(uml::launch_finite_scan(xc, ld, rows, F, e->d_stage, cs));
       launches += 1;
     }
     // (3) score
@@ -906,26 +1267,89 @@ int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_
     l.ld = ld;
     l.n_rows = rows;
     l.labels = e->d_labels + (int64_t)slot * chunk_rows;
+    if (exact && !direct && lossy_capable(src_dtype)) {
+      // flagged rows are re-scored from the caller's own values (the raw chunk is still resident): float64 / int
+      // features that do not survive the fp32 down-cast still get sklearn's float64 labels (_base.py:366-396)
+      l.src.base = raw;
+      l.src.dtype = src_dtype;
+      l.src.row_stride = L.feature_major ? 1 : F;
+      l.src.col_stride = L.feature_major ? rows : 1;
+    }
     rc = enqueue_predict(e, m, l, has_map ? &map : nullptr, mode, false, &launches, &path);
     if (rc != UML_OK) {
       cudaStreamSynchronize(cs);
       cudaStreamSynchronize(e->copy_stream);
       return rc;
     }
-    // (4) labels back
-    UML_CUDA(e, cudaMemcpyAsync(labels_out + r0, l.labels, (size_t)rows * 4, cudaMemcpyDeviceToHost, cs));
-    d2h += rows * 4;
-    UML_CUDA(e, cudaEventRecord(e->chunk_ev[3 + slot], cs));
+    // (4) labels (or class values) back
+    if (values_out) {
+      HOST_CUDA(uml::launch_labels_take(l.labels, 4, rows, e->d_classes, n_classes, e->d_vchunk[slot], cs));
+      launches += 1;
+      HOST_CUDA(cudaMemcpyAsync(values_out + r0, e->d_vchunk[slot], (size_t)rows * 8, cudaMemcpyDeviceToHost, cs));
+      d2h += rows * 8;
+    }
+    if (labels_out) {
+      HOST_CUDA(cudaMemcpyAsync(labels_out + r0, l.labels, (size_t)rows * 4, cudaMemcpyDeviceToHost, cs));
+      d2h += rows * 4;
+    }
+    HOST_CUDA(cudaEventRecord(e->chunk_ev[3 + slot], cs));
     used[slot] = true;
   }
-  UML_CUDA(e, cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
+  HOST_CUDA(cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
+#undef HOST_CUDA
   rc = finish_stats(e, stats, n_rows, launches, path, timed, false);
+  cudaStreamSynchronize(e->copy_stream);
   if (stats) {
     stats->h2d_bytes = h2d;
     stats->d2h_bytes = d2h;
   }
+  // NaN/Inf in the caller's values (the staging kernel checks the source dtype, so a finite float64 that overflows
+  // fp32 is not an error here - exact mode re-scores such rows from the float64 source)
   if (rc == UML_OK && e->h->stage.nonfinite) UML_FAIL(e, UML_ERR_NONFINITE, "Input X contains NaN or infinity.");
   return rc;
+}
+
+int uml_linear_predict_host(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
+                            int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                            int mode, int64_t chunk_rows, uml_stats* stats) {
+  if (!labels_out && n_rows > 0) return UML_ERR_INVALID;
+  return predict_host_impl(e, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, labels_out,
+                           nullptr, nullptr, 0, mode, chunk_rows, stats);
+}
+
+int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
+                                   int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                   const double* classes_host, int n_classes, double* values_out, int mode,
+                                   int64_t chunk_rows, uml_stats* stats) {
+  if ((!values_out && n_rows > 0) || !classes_host || n_classes < 1) return UML_ERR_INVALID;
+  if (m && n_classes < m->dm.n_classes) UML_FAIL(e, UML_ERR_INVALID, "classes_ has %d entries, the model scores %d classes", n_classes, m->dm.n_classes);
+  return predict_host_impl(e, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, nullptr,
+                           values_out, classes_host, n_classes, mode, chunk_rows, stats);
+}
+
+int uml_linear_predict_proba(uml_engine* e, const uml_model* m, const uml_batch* b, float* proba_out, int proba_on_device) {
+  if (!e || !m || !b || (!proba_out && b->n_rows > 0)) return UML_ERR_INVALID;
+  if (b->n_features != m->n_features_in)
+    UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.",
+             b->n_features, m->n_features_in);
+  UML_CUDA(e, cudaSetDevice(e->device));
+  (void)cudaGetLastError();
+  if (b->n_rows == 0) return UML_OK;
+  NvtxRange r_all("uml:predict_proba");
+  const int C = m->dm.n_classes;
+  float* d_out = proba_out;
+  if (!proba_on_device) UML_CUDA(e, cudaMalloc((void**)&d_out, (size_t)b->n_rows * C * 4));
+  cudaError_t ce = uml::launch_linear_proba(m->dm, b->x, b->ld, b->n_rows, d_out, e->info.sm_count, e->stream);
+  if (ce == cudaSuccess && !proba_on_device) {
+    ce = cudaMemcpyAsync(proba_out, d_out, (size_t)b->n_rows * C * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  }
+  if (!proba_on_device) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_out);
+  }
+  if (ce != cudaSuccess) UML_FAIL(e, UML_ERR_CUDA, "uml_linear_predict_proba: %s", cudaGetErrorString(ce));
+  return UML_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -284,6 +284,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
 struct RescoreParams {
   const float* x;
   const double* x64;
+  SrcView src;
   long long ld, ld64;
   long long n_rows;
   const double* w64;
@@ -302,58 +303,253 @@ struct RescoreParams {
 };
 
 
+// one element of the caller's raw source chunk as float64 (exact for every dtype the ABI takes)
+__device__ __forceinline__ double load_src(const SrcView& v, long long row, int f) {
+  const long long i = row * v.row_stride + static_cast<long long>(f) * v.col_stride;
+  switch (v.dtype) {
+    case UML_F64: return static_cast<const double*>(v.base)[i];
+    case UML_I64: return static_cast<double>(static_cast<const long long*>(v.base)[i]);
+    case UML_I32: return static_cast<double>(static_cast<const int*>(v.base)[i]);
+    case UML_U8: return static_cast<double>(static_cast<const unsigned char*>(v.base)[i]);
+    default: return static_cast<double>(static_cast<const float*>(v.base)[i]);
+  }
+}
+
+struct RowScore {
+  int idx;
+  bool bad;        // NaN/Inf in the row
+  bool ambiguous;  // fp64 top-2 margin inside the fp64 rounding bound: a true tie, decided by the first-index rule
+};
+
+// float64 scores of one row by one warp (lanes over features, butterfly sums), first maximum wins like np.argmax.
+// LOAD(f) yields feature f of the row as double.
+template <typename LOAD>
+__device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, const double* __restrict__ b64,
+                                                  int F, int C, int lane) {
+  const double u = 1.1102230246251565e-16;  // 2^-53
+  bool bad = false;
+  double best = 0.0, second = -INFINITY, amax = 0.0;
+  int idx = 0;
+  for (int c = 0; c < C; ++c) {
+    const double* wc = w64 + static_cast<long long>(c) * F;
+    double s = 0.0, a = 0.0;
+    for (int f = lane; f < F; f += 32) {
+      const double xv = load(f);
+      if (c == 0 && !isfinite(xv)) bad = true;
+      const double w = wc[f];
+      s = fma(xv, w, s);
+      a = fma(fabs(xv), fabs(w), a);
+    }
+    s = warp_sum(s) + b64[c];
+    a = warp_sum(a) + fabs(b64[c]);
+    amax = fmax(amax, a);
+    if (c == 0) {
+      best = s;
+    } else if (s > best) {
+      second = best;
+      best = s;
+      idx = c;
+    } else {
+      second = fmax(second, s);
+    }
+  }
+  RowScore r;
+  r.idx = idx;
+  r.bad = __any_sync(0xffffffffu, bad);
+  // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
+  const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
+  r.ambiguous = !((best - second) > 2.0 * err);
+  return r;
+}
+
 __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
   const int F = p.n_features, C = p.n_classes;
-  const double u = 1.1102230246251565e-16;  // 2^-53
   if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
 
   for (long long i = warp_global; i < n; i += warps_total) {
     const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
-    const float* xr = p.x + row * p.ld;
-    const double* xr64 = p.x64 ? p.x64 + row * p.ld64 : nullptr;
-    bool bad = false;
-    double best = 0.0, second = -INFINITY, amax = 0.0;
-    int idx = 0;
-    for (int c = 0; c < C; ++c) {
-      const double* wc = p.w64 + static_cast<long long>(c) * F;
-      double s = 0.0, a = 0.0;
-      for (int f = lane; f < F; f += 32) {
-        const double xv = xr64 ? xr64[f] : static_cast<double>(xr[f]);
-        if (c == 0 && !isfinite(xv)) bad = true;
-        const double w = wc[f];
-        s = fma(xv, w, s);
-        a = fma(fabs(xv), fabs(w), a);
-      }
-      s = warp_sum(s) + p.b64[c];
-      a = warp_sum(a) + fabs(p.b64[c]);
-      amax = fmax(amax, a);
-      if (c == 0) {
-        best = s;
-      } else if (s > best) {
-        second = best;
-        best = s;
-        idx = c;
-      } else {
-        second = fmax(second, s);
-      }
+    RowScore r;
+    if (p.src.base) {
+      const SrcView v = p.src;
+      r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, F, C, lane);
+    } else if (p.x64) {
+      const double* xr64 = p.x64 + row * p.ld64;
+      r = score_row_f64([&](int f) { return xr64[f]; }, p.w64, p.b64, F, C, lane);
+    } else {
+      const float* xr = p.x + row * p.ld;
+      r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, p.w64, p.b64, F, C, lane);
     }
-    bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
-      if (p.labels) p.labels[row] = idx;
+      if (p.labels) p.labels[row] = r.idx;
       for (int q = 0; q < p.n_peers; ++q) {
-        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(idx);
-        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
+        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(r.idx);
+        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = r.idx;
       }
-      if (bad) atomicAdd(&p.counters[1], 1ull);
-      // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
-      const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
-      if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
+      if (r.bad) atomicAdd(&p.counters[1], 1ull);
+      if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
     }
   }
+  // hand the flag list back empty: every block has read *flag_count before it gets here, so the last one to finish may
+  // reset it (and the ticket) for the next scoring launch on this stream - no memset between steps
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&p.counters[3], 1ull);
+    if (ticket == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+      *const_cast<int*>(p.flag_count) = 0;
+      p.counters[3] = 0ull;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small-batch kernel of the online path (fastapi.py:50-64, B <= 64 rows): one warp per row, float64 scores straight
+// from the request's raw feature block (any dtype / order) - no staging pass, no guard, exact by construction
+// ---------------------------------------------------------------------------------------------------------------
+struct SmallParams {
+  SrcView src;
+  const double* w64;
+  const double* b64;
+  int n_classes, n_features, n_rows;
+  SmallResult* out;
+};
+
+__global__ void __launch_bounds__(256) linear_small_kernel(const SmallParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= p.n_rows) return;
+  const SrcView v = p.src;
+  const RowScore r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+  if (lane == 0) {
+    p.out[row].label = r.idx;
+    p.out[row].status = (r.bad ? 1 : 0) | (r.ambiguous ? 2 : 0);
+  }
+}
+
+cudaError_t launch_linear_small(const LinearDeviceModel& m, const SrcView& src, int n_rows, SmallResult* out,
+                                cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  SmallParams p{};
+  p.src = src;
+  p.w64 = m.w64;
+  p.b64 = m.b64;
+  p.n_classes = m.n_classes;
+  p.n_features = m.n_features;
+  p.n_rows = n_rows;
+  p.out = out;
+  linear_small_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// class probabilities: softmax of the fp32 scores (sigmoid for the binary layout, which the model stores expanded as
+// scores [0, s]: softmax([0, s]) = [1 - sigmoid(s), sigmoid(s)], sklearn/linear_model/_logistic.py predict_proba)
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) linear_proba_kernel(const float* __restrict__ x, long long ld, long long n_rows,
+                                                           const float* __restrict__ wt, const float* __restrict__ bias,
+                                                           int F, int cp, float* __restrict__ proba) {
+  extern __shared__ float proba_smem[];
+  float* wt_s = proba_smem;  // [F][cp]
+  for (int i = threadIdx.x; i < F * cp; i += blockDim.x) wt_s[i] = __ldg(wt + i);
+  __syncthreads();
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
+       row += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float* xr = x + row * ld;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = __ldg(bias + c);
+    int f = 0;
+    for (; f + 4 <= F; f += 4) {  // rows are 16-byte aligned (ld % 4 == 0)
+      const float4 v = *reinterpret_cast<const float4*>(xr + f);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float* wrow = wt_s + (f + e) * cp;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(xs[e], wrow[c], acc[c]);
+      }
+    }
+    for (; f < F; ++f) {
+      const float xv = xr[f];
+      const float* wrow = wt_s + f * cp;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(xv, wrow[c], acc[c]);
+    }
+    float mx = acc[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, acc[c]);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[c] = expf(acc[c] - mx);
+      sum += acc[c];
+    }
+    const float inv = 1.0f / sum;
+    float* out = proba + row * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = acc[c] * inv;
+  }
+}
+
+// any number of classes: scores go through the output row (used as scratch), then max / exp / normalise in place
+__global__ void __launch_bounds__(256) linear_proba_generic_kernel(const float* __restrict__ x, long long ld,
+                                                                   long long n_rows, const float* __restrict__ wt,
+                                                                   const float* __restrict__ bias, int F, int C, int cp,
+                                                                   float* __restrict__ proba) {
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
+       row += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float* xr = x + row * ld;
+    float* out = proba + row * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float s = __ldg(bias + c);
+      for (int f = 0; f < F; ++f) s = fmaf(xr[f], __ldg(wt + static_cast<long long>(f) * cp + c), s);
+      out[c] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float e = expf(out[c] - mx);
+      out[c] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / sum;
+    for (int c = 0; c < C; ++c) out[c] *= inv;
+  }
+}
+
+cudaError_t launch_linear_proba(const LinearDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, float* proba,
+                                int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  const long long want = (n_rows + 255) / 256;
+  const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(sm_count) * 8));
+  const size_t smem = static_cast<size_t>(m.n_features) * m.cp * 4;
+  const int F = m.n_features, cp = m.cp;
+  if (m.n_classes <= kMaxClassesTma && smem <= 160 * 1024) {
+    switch (m.n_classes) {
+#define UML_PCASE(N)                                                                                              \
+  case N: {                                                                                                       \
+    auto kern = linear_proba_kernel<N>;                                                                           \
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    if (err != cudaSuccess) return err;                                                                           \
+    kern<<<grid, 256, smem, stream>>>(x, ld, n_rows, m.wt, m.bias, F, cp, proba);                                 \
+    return cudaGetLastError();                                                                                    \
+  }
+      UML_PCASE(2) UML_PCASE(3) UML_PCASE(4) UML_PCASE(5) UML_PCASE(6) UML_PCASE(7) UML_PCASE(8) UML_PCASE(9)
+      UML_PCASE(10) UML_PCASE(11) UML_PCASE(12) UML_PCASE(13) UML_PCASE(14) UML_PCASE(15) UML_PCASE(16)
+#undef UML_PCASE
+      default:
+        break;
+    }
+  }
+  linear_proba_generic_kernel<<<grid, 256, 0, stream>>>(x, ld, n_rows, m.wt, m.bias, F, m.n_classes, cp, proba);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -381,8 +577,12 @@ template <int C, bool EXACT>
 static cudaError_t launch_one(const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
                               cudaStream_t stream) {
   auto kern = linear_argmax_tma_kernel<C, EXACT>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  static size_t configured = 0;  // per instantiation (one device per process): set the attribute once, not per launch
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
   kern<<<grid, kThreads, smem, stream>>>(xmap, p);
   return cudaGetLastError();
 }
@@ -443,6 +643,7 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   RescoreParams p{};
   p.x = l.x;
   p.x64 = l.x64;
+  p.src = l.src;
   p.ld = l.ld;
   p.ld64 = l.ld64;
   p.n_rows = l.n_rows;

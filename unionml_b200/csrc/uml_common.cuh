@@ -38,15 +38,26 @@ struct LinearDeviceModel {
 };
 
 struct FlagList {
-  int* count;        // number of flagged rows appended so far
+  int* count;        // number of flagged rows appended so far; the re-score kernel's last block resets it to 0
   int32_t* rows;     // flagged row indices
   int capacity;
-  unsigned long long* counters;  // [0] = n_ambiguous, [1] = n_nonfinite, [2] = n_flagged
+  unsigned long long* counters;  // [0] = n_ambiguous, [1] = n_nonfinite, [2] = n_flagged, [3] = re-score blocks done
+};
+
+// The caller's own values for the rows of a launch: the raw source chunk as it was copied to the device (any dtype,
+// either memory order).  The fp64 re-score reads the flagged rows from here, so labels follow the float64 (or int64)
+// features the caller passed even when their fp32 copy is lossy (sklearn scores the float64 frame, _base.py:366-396).
+struct SrcView {
+  const void* base;      // nullptr: no view (re-score from x64 or from the fp32 rows)
+  int dtype;             // uml_dtype of the elements
+  long long row_stride;  // in elements
+  long long col_stride;  // in elements
 };
 
 struct LinearLaunch {
   const float* x;       // device fp32 row-major
   const double* x64;    // optional fp64 copy of the same rows (lossy staging), else nullptr
+  SrcView src;          // optional raw source view of the same rows (predict_host), wins over x64
   int64_t ld;           // floats per row
   int64_t ld64;
   int64_t n_rows;
@@ -64,6 +75,17 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
 bool linear_tma_supported(const LinearDeviceModel& m, std::string* why);
 cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,
                                int sm_count, cudaStream_t stream);
+// small-batch kernel of the online path (/predict, B <= 64): warp per row, fp64 straight from the raw source view
+struct SmallResult {  // one per row, written by the kernel, copied back in one piece
+  int32_t label;
+  int32_t status;  // bit 0: NaN/Inf in the row, bit 1: fp64 margin inside the fp64 rounding bound (true tie)
+};
+cudaError_t launch_linear_small(const LinearDeviceModel& m, const SrcView& src, int n_rows, SmallResult* out,
+                                cudaStream_t stream);
+// class probabilities (LogisticRegression.predict_proba, sklearn/linear_model/_logistic.py): softmax of the scores
+// (sigmoid for the binary layout), fp32 scores and exp; proba[n_rows][n_classes] row-major fp32
+cudaError_t launch_linear_proba(const LinearDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, float* proba,
+                                int sm_count, cudaStream_t stream);
 
 // 2-layer MLP (mlp_kernels.cu)
 struct MlpDeviceModel {

@@ -95,13 +95,14 @@ class LinearModel:
         for v in (sh, sc):
             if v is not None and v.shape != (self.n_features,):
                 raise ValueError(f"affine vector must have shape ({self.n_features},)")
-        st = N.lib().uml_linear_set_affine(
-            self.engine._h,
-            self._h,
-            None if sh is None else sh.ctypes.data_as(C.c_void_p),
-            None if sc is None else sc.ctypes.data_as(C.c_void_p),
-        )
-        self.engine._check(st)
+        with self.engine._lock:
+            st = N.lib().uml_linear_set_affine(
+                self.engine._h,
+                self._h,
+                None if sh is None else sh.ctypes.data_as(C.c_void_p),
+                None if sc is None else sc.ctypes.data_as(C.c_void_p),
+            )
+            self.engine._check(st)
 
 
 class MlpModel:
@@ -157,6 +158,7 @@ class Engine:
         self._h = h.value
         self.device = int(device)
         self._lock = threading.Lock()
+        self._stream: Optional[int] = None  # caller's stream handle the engine launches on (None: its own stream)
         self._fin = weakref.finalize(self, lib.uml_engine_destroy, self._h)
         info = N.DeviceInfo()
         self._check(lib.uml_engine_info(self._h, C.byref(info)))
@@ -179,6 +181,12 @@ class Engine:
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run on the caller's stream (e.g. ``torch.cuda.current_stream().cuda_stream``); ``None`` = engine stream."""
         self._check(N.lib().uml_engine_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        self._stream = cuda_stream or None
+
+    @property
+    def stream(self) -> Optional[int]:
+        """The caller's stream handle set by :meth:`set_stream`, or ``None`` when the engine runs on its own stream."""
+        return self._stream
 
     def synchronize(self) -> None:
         self._check(N.lib().uml_engine_synchronize(self._h))
@@ -214,16 +222,17 @@ class Engine:
         if intercept.shape != (n_classes,):
             raise ValueError(f"intercept shape {intercept.shape} does not match coef {coef.shape}")
         h = C.c_void_p()
-        st = N.lib().uml_linear_load(
-            self._h,
-            C.byref(h),
-            coef.ctypes.data_as(C.c_void_p),
-            intercept.ctypes.data_as(C.c_void_p),
-            n_classes,
-            n_features,
-            N.UML_F32 if dt == np.float32 else N.UML_F64,
-        )
-        self._check(st)
+        with self._lock:
+            st = N.lib().uml_linear_load(
+                self._h,
+                C.byref(h),
+                coef.ctypes.data_as(C.c_void_p),
+                intercept.ctypes.data_as(C.c_void_p),
+                n_classes,
+                n_features,
+                N.UML_F32 if dt == np.float32 else N.UML_F64,
+            )
+            self._check(st)
         return LinearModel(self, h.value, n_features, max(n_classes, 2), None if classes is None else np.asarray(classes))
 
     def load_mlp(self, w1, b1, w2, b2) -> MlpModel:
@@ -234,10 +243,11 @@ class Engine:
         if b1.shape != (n_hidden,) or w2.shape != (n_out, n_hidden) or b2.shape != (n_out,):
             raise ValueError(f"inconsistent MLP shapes {w1.shape} {b1.shape} {w2.shape} {b2.shape}")
         h = C.c_void_p()
-        st = N.lib().uml_mlp_load(
-            self._h, C.byref(h), *(a.ctypes.data_as(C.c_void_p) for a in (w1, b1, w2, b2)), n_in, n_hidden, n_out
-        )
-        self._check(st)
+        with self._lock:
+            st = N.lib().uml_mlp_load(
+                self._h, C.byref(h), *(a.ctypes.data_as(C.c_void_p) for a in (w1, b1, w2, b2)), n_in, n_hidden, n_out
+            )
+            self._check(st)
         return MlpModel(self, h.value, n_in, n_hidden, n_out)
 
     def predict_mlp(self, model: MlpModel, batch: Batch, exact: bool = True, out_device_ptr: Optional[int] = None,
@@ -256,7 +266,7 @@ class Engine:
             st = N.lib().uml_mlp_predict(
                 self._h, model._h, batch._h, out.ctypes.data_as(C.c_void_p), 0, mode, C.byref(stats) if stats else None
             )
-        self._check(st)
+            self._check(st)  # under the lock: uml_last_error is per engine, another thread's call may overwrite it
         return out, stats.as_dict() if stats else None
 
     def stage(self, features: Any, keep_f64: bool = True, check_finite: bool = True) -> Batch:
@@ -276,16 +286,17 @@ class Engine:
                 _DTYPES[arr.dtype],
                 flags,
             )
-        self._check(st)
+            self._check(st)
         return Batch(self, h.value)
 
     def wrap_device(self, device_ptr: int, n_rows: int, n_features: int, ld: Optional[int] = None, keepalive: Any = None) -> Batch:
         """Wrap fp32 row-major rows that already live in HBM (e.g. a torch CUDA tensor's ``data_ptr()``)."""
         h = C.c_void_p()
-        st = N.lib().uml_batch_from_device(
-            self._h, C.byref(h), C.c_void_p(device_ptr), n_rows, n_features, ld if ld is not None else n_features
-        )
-        self._check(st)
+        with self._lock:
+            st = N.lib().uml_batch_from_device(
+                self._h, C.byref(h), C.c_void_p(device_ptr), n_rows, n_features, ld if ld is not None else n_features
+            )
+            self._check(st)
         return Batch(self, h.value, keepalive)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -311,7 +322,7 @@ class Engine:
             st = N.lib().uml_linear_predict(
                 self._h, model._h, batch._h, out.ctypes.data_as(C.c_void_p), 0, mode, C.byref(stats) if stats else None
             )
-        self._check(st)
+            self._check(st)
         return out, stats.as_dict() if stats else None
 
     def predict_peers(self, model: LinearModel, batch: Batch, peer_ptrs, row_offset: int, exact: bool = True,
@@ -324,7 +335,7 @@ class Engine:
             st = N.lib().uml_linear_predict_peers(
                 self._h, model._h, batch._h, arr, len(peer_ptrs), row_offset, label_bytes, mode, C.byref(stats) if stats else None
             )
-        self._check(st)
+            self._check(st)
         return stats.as_dict() if stats else None
 
     def take_labels(self, labels_ptr: int, n: int, classes, label_bytes: int = 4) -> np.ndarray:
@@ -334,7 +345,7 @@ class Engine:
         with self._lock:
             st = N.lib().uml_labels_take(self._h, C.c_void_p(labels_ptr), label_bytes, n,
                                          classes.ctypes.data_as(C.c_void_p), len(classes), out.ctypes.data_as(C.c_void_p))
-        self._check(st)
+            self._check(st)
         return out
 
     def count_equal(self, labels_ptr: int, n: int, classes, targets, label_bytes: int = 4) -> int:
@@ -348,7 +359,7 @@ class Engine:
             st = N.lib().uml_labels_count_equal(self._h, C.c_void_p(labels_ptr), label_bytes, n,
                                                 classes.ctypes.data_as(C.c_void_p), len(classes),
                                                 targets.ctypes.data_as(C.c_void_p), C.byref(cnt))
-        self._check(st)
+            self._check(st)
         return int(cnt.value)
 
     def push_labels(self, src_ptr: int, dst_ptrs, nbytes: int) -> None:
@@ -357,7 +368,7 @@ class Engine:
         arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(p) for p in dst_ptrs])
         with self._lock:
             st = N.lib().uml_labels_push(self._h, C.c_void_p(src_ptr), arr, len(dst_ptrs), nbytes)
-        self._check(st)
+            self._check(st)
 
     def predict_host(
         self,
@@ -389,8 +400,46 @@ class Engine:
                 chunk_rows,
                 C.byref(stats),
             )
-        self._check(st)
+            self._check(st)
         return out, stats.as_dict()
+
+    def predict_host_values(self, model: LinearModel, features: Any, classes, exact: bool = True,
+                            chunk_rows: int = 0) -> Tuple[np.ndarray, dict]:
+        """Host rows -> ``classes_[argmax]`` as a float64 host vector: the pipelined call with ``classes_.take`` and the
+        float conversion of the canonical predictor (``README.md:92``) done on the device, chunk by chunk."""
+        arr = as_feature_array(features)
+        classes = np.ascontiguousarray(classes, dtype=np.float64)
+        out = np.empty(arr.shape[0], dtype=np.float64)
+        stats = N.Stats()
+        with self._lock:
+            st = N.lib().uml_linear_predict_host_values(
+                self._h,
+                model._h,
+                C.c_void_p(arr.ctypes.data),
+                arr.shape[0],
+                arr.shape[1],
+                arr.strides[0],
+                arr.strides[1],
+                _DTYPES[arr.dtype],
+                classes.ctypes.data_as(C.c_void_p),
+                len(classes),
+                out.ctypes.data_as(C.c_void_p),
+                N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST,
+                chunk_rows,
+                C.byref(stats),
+            )
+            self._check(st)
+        return out, stats.as_dict()
+
+    def predict_proba(self, model: LinearModel, batch: Batch, out_device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        """``softmax(X @ coef_.T + intercept_)`` per row (fp32), ``(n_rows, n_classes)``; ``[1 - p, p]`` for a binary model."""
+        with self._lock:
+            if out_device_ptr is not None:
+                self._check(N.lib().uml_linear_predict_proba(self._h, model._h, batch._h, C.c_void_p(out_device_ptr), 1))
+                return None
+            out = np.empty((batch.n_rows, model.n_classes), dtype=np.float32)
+            self._check(N.lib().uml_linear_predict_proba(self._h, model._h, batch._h, out.ctypes.data_as(C.c_void_p), 0))
+        return out
 
 
 _default_engine: Optional[Engine] = None

@@ -31,6 +31,25 @@ def _exact_default() -> bool:
     return os.environ.get("UNIONML_B200_MODE", "exact").lower() != "fast"
 
 
+def _check_linear_classifier(clf) -> None:
+    """Only a *classifier* with dense ``coef_`` is an argmax model: a regressor (``LinearRegression``, ``Ridge``) also
+    has ``coef_``/``intercept_`` and would silently come back as class indices."""
+    has_classes = hasattr(clf, "classes_")
+    try:
+        from sklearn.base import is_classifier
+
+        ok = is_classifier(clf) or has_classes
+    except Exception:  # sklearn absent: duck-type on classes_
+        ok = has_classes
+    if not ok:
+        raise TypeError(
+            f"linear_argmax scores linear *classifiers* (coef_, intercept_, classes_); {type(clf).__name__} is not one"
+        )
+    coef = getattr(clf, "coef_", None)
+    if coef is not None and hasattr(coef, "toarray"):
+        raise TypeError("linear_argmax needs a dense coef_ (call estimator.densify() first)")
+
+
 def _check_fitted(estimator) -> None:
     if not hasattr(estimator, "coef_") or not hasattr(estimator, "intercept_"):
         from sklearn.exceptions import NotFittedError
@@ -83,18 +102,38 @@ def unwrap_pipeline(estimator):
     return clf, (None if shift is None else np.asarray(shift, dtype=np.float64)), scale
 
 
+def _weights_key(clf, shift, scale) -> tuple:
+    """Identity of the arrays + a few cheap fingerprints (in-place edits of coef_ change the sum)."""
+    coef, intercept = clf.coef_, clf.intercept_
+    return (
+        id(coef), id(intercept), getattr(coef, "shape", None), str(getattr(coef, "dtype", "")),
+        float(np.sum(coef)), float(np.sum(intercept)), float(np.asarray(coef).flat[0]), float(np.asarray(coef).flat[-1]),
+        None if shift is None else hash(np.asarray(shift).tobytes()),
+        None if scale is None else hash(np.asarray(scale).tobytes()),
+    )
+
+
 def device_model(estimator, engine: Engine | None = None) -> LinearModel:
     """The estimator's ``coef_``/``intercept_`` (with a leading StandardScaler folded in) staged on the device, cached
     per estimator object and weights."""
+    engine = engine or get_engine()
+    # fast path of the online route: same estimator object, same coef_/intercept_ array objects (sklearn's fit
+    # rebinds them), unchanged first/last/sum fingerprints - no re-hash of the weights per request
+    with _cache_lock:
+        try:
+            hit = _model_cache.get(estimator)
+        except TypeError:
+            hit = None
+    if hit is not None and getattr(estimator, "steps", None) is None:  # bare classifier (a Pipeline re-derives its scaler)
+        key, dm = hit[0], hit[1]
+        if key[0] == id(engine) and hasattr(estimator, "coef_") and key[1:] == _weights_key(estimator, None, None):
+            return dm
     clf, shift, scale = unwrap_pipeline(estimator)
     _check_fitted(clf)
-    engine = engine or get_engine()
+    _check_linear_classifier(clf)
     coef = np.asarray(clf.coef_)
     intercept = np.asarray(clf.intercept_)
-    key = (
-        id(engine), coef.shape, coef.dtype.str, hash(coef.tobytes()), hash(intercept.tobytes()),
-        None if shift is None else hash(shift.tobytes()), None if scale is None else hash(scale.tobytes()),
-    )
+    key = (id(engine),) + _weights_key(clf, shift, scale)
     with _cache_lock:
         try:
             hit = _model_cache.get(estimator)
@@ -112,12 +151,51 @@ def device_model(estimator, engine: Engine | None = None) -> LinearModel:
         return dm
 
 
+#: rows of the last calls whose float64 top-2 margin was inside the float64 rounding bound (true ties / sub-1e-13
+#: gaps): numpy's first-index rule decides them here exactly as ``np.argmax`` does, but a BLAS with another summation
+#: order may round such a row the other way.  Surfaced (not buried): ``last_ambiguous_rows()`` + a one-time warning.
+_ambiguous = {"last": 0, "total": 0, "warned": False}
+
+
+def last_ambiguous_rows() -> int:
+    return _ambiguous["last"]
+
+
+def _note_ambiguous(stats) -> None:
+    n = int(stats.get("n_ambiguous", 0)) if stats else 0
+    _ambiguous["last"] = n
+    if n:
+        _ambiguous["total"] += n
+        if not _ambiguous["warned"]:
+            _ambiguous["warned"] = True
+            import warnings
+
+            warnings.warn(
+                f"unionml_b200: {n} row(s) have float64 scores tied within rounding (top-2 margin < ~1e-13 relative); "
+                "their label follows numpy's first-maximum rule and may differ from a BLAS with another summation "
+                "order. See unionml_b200.predictors.last_ambiguous_rows().",
+                RuntimeWarning,
+                stacklevel=3,
+            )
+
+
+def _check_min_samples(features) -> None:
+    """sklearn's ``check_array`` refuses an empty batch (``sklearn/utils/validation.py``, ensure_min_samples=1)."""
+    shape = getattr(features, "shape", None)
+    if shape is not None and len(shape) == 2 and shape[0] == 0:
+        raise ValueError(
+            f"Found array with 0 sample(s) (shape={tuple(shape)}) while a minimum of 1 is required."
+        )
+
+
 def linear_predict_labels(estimator, features, exact: bool | None = None, engine: Engine | None = None) -> np.ndarray:
     """``estimator.predict(features)`` on the GPU: ndarray of class labels (``classes_`` dtype)."""
     engine = engine or get_engine()
     dm = device_model(estimator, engine)
     _check_feature_names(estimator, features)
-    idx, _stats = engine.predict_host(dm, features, exact=_exact_default() if exact is None else exact)
+    _check_min_samples(features)
+    idx, stats = engine.predict_host(dm, features, exact=_exact_default() if exact is None else exact)
+    _note_ambiguous(stats)
     classes = getattr(estimator, "classes_", None)  # a Pipeline forwards classes_ of its final step
     if classes is None:
         return idx.astype(np.int64)
@@ -145,8 +223,35 @@ def linear_accuracy(estimator: Any, features: Any, target: Any, exact: bool | No
 
 
 def linear_argmax(estimator: Any, features: Any) -> List[float]:
-    """Drop-in body for ``@model.predictor``: class labels as Python floats."""
-    return linear_predict_labels(estimator, features).astype(np.float64).tolist()
+    """Drop-in body for ``@model.predictor``: class labels as Python floats.
+
+    Numeric ``classes_`` (the canonical case): ``classes_.take`` and the float conversion run on the device
+    (``uml_linear_predict_host_values``) and the float64 vector becomes the list in one ``tolist()``."""
+    classes = getattr(estimator, "classes_", None)
+    if classes is not None and np.asarray(classes).dtype.kind in "iufb":
+        engine = get_engine()
+        dm = device_model(estimator, engine)
+        _check_feature_names(estimator, features)
+        _check_min_samples(features)
+        values, stats = engine.predict_host_values(dm, features, np.asarray(classes, dtype=np.float64), exact=_exact_default())
+        _note_ambiguous(stats)
+        return values.tolist()
+    return [float(x) for x in linear_predict_labels(estimator, features)]
+
+
+def linear_predict_proba(estimator: Any, features: Any) -> np.ndarray:
+    """``estimator.predict_proba(features)`` on the GPU (``sklearn/linear_model/_logistic.py`` predict_proba: softmax of
+    the decision function, sigmoid columns ``[1 - p, p]`` for a binary model).  fp32 arithmetic: agrees with
+    scikit-learn's float64 probabilities to ~1e-6 absolute (the tests state the tolerance)."""
+    engine = get_engine()
+    dm = device_model(estimator, engine)
+    _check_feature_names(estimator, features)
+    _check_min_samples(features)
+    batch = engine.stage(features, keep_f64=False)
+    try:
+        return engine.predict_proba(dm, batch)
+    finally:
+        batch.free()
 
 
 # ---------------------------------------------------------------------------------------------------------------
