@@ -73,7 +73,8 @@ typedef struct uml_stats {
   int64_t h2d_bytes;
   int64_t d2h_bytes;
   int32_t kernel_launches; /* kernels of this library launched by the call                                            */
-  int32_t path;            /* 1 = TMA fp32 tile kernel, 2 = generic fp64 kernel, 3 = MLP kernel, 4 = small-batch fp64
+  int32_t path;            /* 1 = TMA fp32 tile kernel, 2 = generic fp64 kernel, 3 = MLP CUDA-core kernel, 5 = MLP tensor-core
+                              (tcgen05) kernel, 4 = small-batch fp64
                               kernel of the online path (<= 64 rows, one CUDA graph: H2D, kernel, D2H)                 */
 } uml_stats;
 
@@ -182,6 +183,13 @@ UML_API int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const fl
 UML_API void uml_mlp_free(uml_mlp* m);
 UML_API int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
                     int mode, uml_stats* stats);
+
+/* fused compute + collective for the MLP predictor: same contract as uml_linear_predict_peers (labels of this rank's
+ * rows are stored into every entry of peer_labels at row_offset from the kernel epilogue; int32 or uint8 vectors).
+ * Batches whose features are tf32 values (integer / pixel domains) run layer 1 on the tensor cores (tcgen05, stats
+ * path 5); other batches take the CUDA-core kernel (path 3) and a thin scatter kernel. */
+UML_API int uml_mlp_predict_peers(uml_engine* e, const uml_mlp* m, const uml_batch* b, void* const* peer_labels, int n_peers,
+                          int64_t row_offset, int label_bytes, int mode, uml_stats* stats);
 
 #ifdef __cplusplus
 }

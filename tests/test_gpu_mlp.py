@@ -35,7 +35,7 @@ def test_golden_fixture_equals_torch_labels(engine, mlp_golden):
     b = engine.stage(mlp_golden["X"])
     got, st = engine.predict_mlp(m, b, exact=True)
     np.testing.assert_array_equal(got, mlp_golden["labels_torch"])
-    assert st["path"] == 3 and st["kernel_launches"] == 2
+    assert st["path"] == 5 and st["kernel_launches"] == 2  # integer pixel rows are tf32 values: tensor-core kernel
 
 
 @pytest.mark.parametrize("rows", [1, 127, 128, 129, 5000, 250_001])
@@ -92,6 +92,105 @@ def test_against_torch_cpu_module_and_predictor(mlp_golden):
     # torch's own fp32 forward is only trusted outside its rounding noise; inside it the float64 network decides
     margin = omlp.logit_margin_f64(frame.values, *_weights(mlp_golden))
     assert all(margin[i] < 1e-4 for i in mism) and len(mism) <= 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, kind::tf32) kernel: stats path 5
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 5000, 250_001])
+def test_tensor_core_path_parity_and_dispatch(engine, mlp_golden, rows, monkeypatch):
+    """Integer / pixel rows are tf32 values -> layer 1 on the tensor cores; general floats -> the CUDA-core kernel.
+    Both equal the float64 network on every row."""
+    w = _weights(mlp_golden)
+    m = engine.load_mlp(*w)
+    Xi = np.random.default_rng(rows).integers(0, 256, size=(rows, 64)).astype(np.float32)  # MNIST pixel domain
+    got, st = engine.predict_mlp(m, engine.stage(Xi), exact=True)
+    np.testing.assert_array_equal(got, omlp.predict_indices_f64(Xi, *w).astype(np.int32))
+    assert st["path"] == 5
+    Xf = np.random.default_rng(rows).standard_normal((rows, 64)).astype(np.float32)
+    got, st = engine.predict_mlp(m, engine.stage(Xf), exact=True)
+    np.testing.assert_array_equal(got, omlp.predict_indices_f64(Xf, *w).astype(np.int32))
+    assert st["path"] == 3
+    # forcing the CUDA-core kernel on the integer rows gives the same labels
+    monkeypatch.setenv("UML_B200_MLP_TC", "0")
+    got0, st0 = engine.predict_mlp(m, engine.stage(Xi), exact=True)
+    assert st0["path"] == 3
+    np.testing.assert_array_equal(got0, omlp.predict_indices_f64(Xi, *w).astype(np.int32))
+
+
+def test_tensor_core_kernel_is_safe_on_rows_that_are_not_tf32(engine, mlp_golden, monkeypatch):
+    """Forced onto general floats the kernel scores truncated inputs - and knows it: every such row gets A1 = +inf,
+    is flagged and re-scored in fp64, so the labels are still the float64 network's."""
+    w = _weights(mlp_golden)
+    m = engine.load_mlp(*w)
+    rng = np.random.default_rng(12)
+    X = rng.integers(0, 17, size=(200_000, 64)).astype(np.float32)
+    dirty = rng.choice(200_000, size=5_000, replace=False)
+    X[dirty, rng.integers(0, 64, size=5_000)] += np.float32(1.0 / 3.0)  # not representable in 10 mantissa bits
+    want = omlp.predict_indices_f64(X, *w).astype(np.int32)
+    monkeypatch.setenv("UML_B200_MLP_TC", "1")
+    got, st = engine.predict_mlp(m, engine.stage(X), exact=True)
+    assert st["path"] == 5 and st["n_flagged"] >= 5_000
+    np.testing.assert_array_equal(got, want)
+    Xf = rng.standard_normal((50_000, 64)).astype(np.float32)
+    got, st = engine.predict_mlp(m, engine.stage(Xf), exact=True)
+    assert st["path"] == 5 and st["n_flagged"] == 50_000
+    np.testing.assert_array_equal(got, omlp.predict_indices_f64(Xf, *w).astype(np.int32))
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 10), (64, 16, 10), (50, 32, 3), (32, 16, 2), (128, 32, 10), (100, 16, 3)])
+def test_tensor_core_shapes(engine, shape):
+    F, H, C = shape
+    rng = np.random.default_rng(F * 1000 + H * 10 + C)
+    w1, b1 = (rng.standard_normal((H, F)) * 0.2).astype(np.float32), rng.standard_normal(H).astype(np.float32)
+    w2, b2 = rng.standard_normal((C, H)).astype(np.float32), rng.standard_normal(C).astype(np.float32)
+    X = rng.integers(-8, 9, size=(70_001, F)).astype(np.float32)
+    m = engine.load_mlp(w1, b1, w2, b2)
+    got, st = engine.predict_mlp(m, engine.stage(X), exact=True)
+    np.testing.assert_array_equal(got, omlp.predict_indices_f64(X, w1, b1, w2, b2).astype(np.int32))
+    assert st["path"] == 5, st
+    fast, stf = engine.predict_mlp(m, engine.stage(X), exact=False)
+    assert stf["path"] == 5 and (fast != got).sum() <= st["n_flagged"]
+
+
+def test_tensor_core_full_size_ten_million(engine, mlp_golden):
+    """cfg 5 at BASELINE size: all 10M labels against the float64 network, streamed in 1M-row chunks."""
+    w = _weights(mlp_golden)
+    m = engine.load_mlp(*w)
+    N = 10_000_000
+    X = engine.pinned_empty((N, 64), np.float32)
+    for k in range(10):
+        X[k * 1_000_000 : (k + 1) * 1_000_000] = np.random.default_rng(k).integers(0, 17, size=(1_000_000, 64), dtype=np.uint8)
+    b = engine.stage(X)
+    labels, st = engine.predict_mlp(m, b, exact=True)
+    assert st["path"] == 5 and st["n_rows"] == N and st["n_ambiguous"] == 0 and st["n_flagged"] < N // 50
+    for k in range(10):
+        sl = slice(k * 1_000_000, (k + 1) * 1_000_000)
+        np.testing.assert_array_equal(labels[sl], omlp.predict_indices_f64(X[sl], *w).astype(np.int32))
+    fast, _ = engine.predict_mlp(m, b, exact=False)
+    assert (fast != labels).sum() <= st["n_flagged"]
+    print(f"mlp tcgen05 10M x 64: kernel {st['kernel_ms']:.3f} ms, re-score {st['recheck_ms']:.3f} ms, flagged {st['n_flagged']}")
+
+
+def test_mlp_peer_label_vectors(engine, mlp_golden, monkeypatch):
+    """uml_mlp_predict_peers: labels land in every target vector (uint8 and int32 wire), both kernels."""
+    w = _weights(mlp_golden)
+    m = engine.load_mlp(*w)
+    rows = 100_003
+    X = np.random.default_rng(2).integers(0, 17, size=(rows, 64)).astype(np.float32)
+    want = omlp.predict_indices_f64(X, *w).astype(np.int32)
+    b = engine.stage(X)
+    for force in ("1", "0"):
+        monkeypatch.setenv("UML_B200_MLP_TC", force)
+        for lb, dt in ((1, torch.uint8), (4, torch.int32)):
+            v0 = torch.full((rows + 64,), 77, dtype=dt, device="cuda")
+            v1 = torch.full((rows + 64,), 77, dtype=dt, device="cuda")
+            st = engine.predict_mlp_peers(m, b, [v0.data_ptr(), v1.data_ptr()], 32, exact=True, want_stats=True, label_bytes=lb)
+            assert st["path"] == (5 if force == "1" else 3)
+            for v in (v0, v1):
+                host = v.cpu().numpy().astype(np.int32)
+                np.testing.assert_array_equal(host[32 : 32 + rows], want)
+                assert (host[:32] == 77).all() and (host[32 + rows :] == 77).all()
 
 
 def test_generic_shapes_take_the_fp64_kernel(engine):

@@ -1,6 +1,7 @@
 // C ABI of the uml_b200 engine (see include/uml_b200.h): device binding, model/batch residency, predict calls.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -203,6 +204,7 @@ struct uml_batch {
   int n_features = 0;
   bool owns = false;
   bool lossless = true;
+  int tf32_exact = -1;  // every fp32 feature is a tf32 value: 1 yes, 0 no, -1 not scanned yet (wrapped device rows)
   bool has_map = false;
   CUtensorMap map{};  // boxes of 128 rows x 32 features
 };
@@ -215,6 +217,8 @@ struct uml_mlp {
   float* d_w2t = nullptr;
   float* d_b2 = nullptr;
   double* d_w64 = nullptr;  // w1 | b1 | w2 | b2 packed
+  float* d_w1_tiles = nullptr;  // tensor-core B operand: tf32 hi | lo rows, pre-swizzled
+  uml::MlpHostModel host;
 };
 
 #define UML_FAIL(E, CODE, ...)                              \
@@ -604,6 +608,69 @@ static cudaError_t copy_chunk_h2d(void* dst, const void* host, const SrcLayout& 
   return cudaMemcpy2DAsync(dst, width, src + (size_t)r0 * L.elem, spitch, width, (size_t)F, cudaMemcpyHostToDevice, s);
 }
 
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static bool lossy_capable(int dtype) { return dtype == UML_F64 || dtype == UML_I64 || dtype == UML_I32; }
+
+// gather tasks for rows [r0, r0+rows) of the host source into a compact chunk (row-major [rows][F] or feature-major
+// [F][rows]) at `dst`; contiguous runs are cut into <= 1 MiB pieces so the pool's threads share them
+static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, const void* host, const SrcLayout& L,
+                               int64_t r0, int64_t rows, int F) {
+  tasks.clear();
+  const char* src = (const char*)host;
+  const size_t piece = 1u << 20;
+  auto add_run = [&](char* d, const char* s_, size_t n) {
+    for (size_t o = 0; o < n; o += piece) tasks.push_back({d + o, s_ + o, std::min(piece, n - o)});
+  };
+  if (!L.feature_major) {
+    const size_t width = (size_t)F * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
+    if (spitch == width) {
+      add_run(dst, src + (size_t)r0 * spitch, width * (size_t)rows);
+    } else {
+      // strided rows (a column slice of a wider C-order array): blocks of rows, each row its own run
+      const int64_t rows_per_task = std::max<int64_t>(1, (int64_t)(piece / width));
+      for (int64_t r = 0; r < rows; r += rows_per_task) {
+        const int64_t n = std::min(rows_per_task, rows - r);
+        tasks.push_back({dst + (size_t)r * width, src + (size_t)(r0 + r) * spitch, width, (size_t)n, width, spitch});
+      }
+    }
+  } else {
+    const size_t run = (size_t)rows * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
+    for (int f = 0; f < F; ++f) add_run(dst + (size_t)f * run, src + (size_t)f * spitch + (size_t)r0 * L.elem, run);
+  }
+}
+
+// pinned bounce buffers (3 slots) + the copy pool, created on first use
+static int ensure_bounce(uml_engine* e, int64_t bytes) {
+  if (e->bounce_cap < bytes) {
+    for (auto& p : e->h_bounce) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+    }
+    e->bounce_cap = 0;
+    for (auto& p : e->h_bounce) UML_CUDA(e, cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault));
+    e->bounce_cap = bytes;
+  }
+  if (!e->pool) {
+    int n = 0;
+    if (const char* env = getenv("UML_B200_COPY_THREADS")) n = atoi(env);
+    if (n <= 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, std::thread::hardware_concurrency() / 4u));
+    e->pool = new CopyPool(n - 1);  // the calling thread is the n-th worker
+  }
+  return UML_OK;
+}
+
+static bool want_bounce(const void* host_ptr, int64_t bytes) {
+  return bytes >= (8ll << 20) && !host_ptr_is_pinned(host_ptr) && !getenv("UML_B200_NO_BOUNCE");
+}
+
 int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t n_rows, int n_features,
                    int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, uint32_t flags) {
   if (!e || !out || (!host_ptr && n_rows > 0) || n_rows < 0 || n_features < 1) return UML_ERR_INVALID;
@@ -659,9 +726,11 @@ int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t
   } while (0)
   STAGE_CUDA(cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), cs));
 
-  const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld;
+  // already the resident layout and page-locked: one straight H2D, then the finiteness scan (a large pageable source
+  // goes through the chunked path instead, where host threads feed pinned bounce buffers)
+  const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld &&
+                      !want_bounce(host_ptr, n_rows * (int64_t)F * L.elem);
   if (direct) {
-    // already the resident layout: one straight H2D, then the finiteness scan
     STAGE_CUDA(cudaMemcpyAsync(b->x, host_ptr, (size_t)n_rows * ld * 4, cudaMemcpyHostToDevice, cs));
     if (check) STAGE_CUDA(uml::launch_finite_scan(b->x, ld, n_rows, F, e->d_stage, cs));
   } else {
@@ -671,11 +740,22 @@ int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t
     chunk_rows = std::min<int64_t>((chunk_rows + 31) / 32 * 32, std::max<int64_t>(n_rows, 1));
     int rc2 = ensure_chunks(e, chunk_rows * row_bytes);
     if (rc2 != UML_OK) return bail(rc2);
+    // pageable frames: a few host threads gather each chunk into a pinned bounce buffer (see CopyPool)
+    const bool bounce = want_bounce(host_ptr, n_rows * row_bytes);
+    if (bounce && (rc2 = ensure_bounce(e, chunk_rows * row_bytes)) != UML_OK) return bail(rc2);
+    std::vector<CopyPool::Task> tasks;
     int slot = 0;
     bool used[3] = {false, false, false};
     for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
       const int64_t rows = std::min(chunk_rows, n_rows - r0);
       if (used[slot]) STAGE_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));  // convert done
+      if (bounce) {
+        if (used[slot]) STAGE_CUDA(cudaEventSynchronize(e->chunk_ev[slot]));  // previous H2D has left the bounce buffer
+        build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F);
+        e->pool->run(tasks);
+        STAGE_CUDA(cudaMemcpyAsync(e->d_chunk[slot], e->h_bounce[slot], (size_t)(rows * row_bytes), cudaMemcpyHostToDevice,
+                                   e->copy_stream));
+      } else
       STAGE_CUDA(copy_chunk_h2d(e->d_chunk[slot], host_ptr, L, r0, rows, F, e->copy_stream));
       STAGE_CUDA(cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
       STAGE_CUDA(cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
@@ -694,6 +774,7 @@ int uml_stage_rows(uml_engine* e, uml_batch** out, const void* host_ptr, int64_t
     return bail(UML_ERR_NONFINITE);
   }
   b->lossless = direct ? true : e->h->stage.lossy == 0;
+  if (check || !direct) b->tf32_exact = e->h->stage.not_tf32 == 0 ? 1 : 0;  // the scan / conversion pass saw every value
   if (b->x64 && b->lossless) {
     cudaFree(b->x64);
     b->x64 = nullptr;
@@ -973,45 +1054,6 @@ int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst,
 // ---------------------------------------------------------------------------------------------------------------
 // host rows -> host labels
 // ---------------------------------------------------------------------------------------------------------------
-static bool host_ptr_is_pinned(const void* p) {
-  cudaPointerAttributes a{};
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
-
-static bool lossy_capable(int dtype) { return dtype == UML_F64 || dtype == UML_I64 || dtype == UML_I32; }
-
-// gather tasks for rows [r0, r0+rows) of the host source into a compact chunk (row-major [rows][F] or feature-major
-// [F][rows]) at `dst`; contiguous runs are cut into <= 1 MiB pieces so the pool's threads share them
-static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, const void* host, const SrcLayout& L,
-                               int64_t r0, int64_t rows, int F) {
-  tasks.clear();
-  const char* src = (const char*)host;
-  const size_t piece = 1u << 20;
-  auto add_run = [&](char* d, const char* s_, size_t n) {
-    for (size_t o = 0; o < n; o += piece) tasks.push_back({d + o, s_ + o, std::min(piece, n - o)});
-  };
-  if (!L.feature_major) {
-    const size_t width = (size_t)F * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
-    if (spitch == width) {
-      add_run(dst, src + (size_t)r0 * spitch, width * (size_t)rows);
-    } else {
-      // strided rows (a column slice of a wider C-order array): blocks of rows, each row its own run
-      const int64_t rows_per_task = std::max<int64_t>(1, (int64_t)(piece / width));
-      for (int64_t r = 0; r < rows; r += rows_per_task) {
-        const int64_t n = std::min(rows_per_task, rows - r);
-        tasks.push_back({dst + (size_t)r * width, src + (size_t)(r0 + r) * spitch, width, (size_t)n, width, spitch});
-      }
-    }
-  } else {
-    const size_t run = (size_t)rows * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
-    for (int f = 0; f < F; ++f) add_run(dst + (size_t)f * run, src + (size_t)f * spitch + (size_t)r0 * L.elem, run);
-  }
-}
-
 // B <= kSmallRows: request block -> pinned buffer -> (graph: H2D, linear_small_kernel, D2H) -> labels.  fp64 from the
 // caller's own values, so the result is the exact-mode result for either mode.
 static int predict_host_small(uml_engine* e, const uml_model* m, const void* host_ptr, int n_rows, int F,
@@ -1035,10 +1077,17 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
       if (spitch == width) memcpy(dst, src, bytes);
       else for (int r = 0; r < n_rows; ++r) memcpy(dst + (size_t)r * width, src + (size_t)r * spitch, width);
     } else {
-      const size_t spitch = (size_t)L.pitch_elems * L.elem;
-      for (int f = 0; f < F; ++f)
-        for (int r = 0; r < n_rows; ++r)
-          memcpy(dst + (size_t)r * width + (size_t)f * L.elem, src + (size_t)f * spitch + (size_t)r * L.elem, L.elem);
+      // feature-major request (a pandas block): typed transpose into rows
+      const size_t pitch = (size_t)L.pitch_elems;
+      auto transpose = [&](auto* d, const auto* s_) {
+        for (int f = 0; f < F; ++f)
+          for (int r = 0; r < n_rows; ++r) d[(size_t)r * F + f] = s_[(size_t)f * pitch + r];
+      };
+      switch (L.elem) {
+        case 8: transpose((uint64_t*)dst, (const uint64_t*)src); break;
+        case 4: transpose((uint32_t*)dst, (const uint32_t*)src); break;
+        default: transpose((uint8_t*)dst, (const uint8_t*)src); break;
+      }
     }
   }
   uml::SrcView view{e->d_req, src_dtype, (long long)F, 1};
@@ -1139,7 +1188,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   chunk_rows = std::min<int64_t>((chunk_rows + 127) / 128 * 128, (n_rows + 127) / 128 * 128);
   const bool direct = !L.feature_major && src_dtype == UML_F32 && L.pitch_elems == ld;
   // pageable sources of any size worth the trouble go through pinned bounce buffers filled by the copy pool
-  const bool bounce = n_rows * row_bytes >= (8ll << 20) && !host_ptr_is_pinned(host_ptr) && !getenv("UML_B200_NO_BOUNCE");
+  const bool bounce = want_bounce(host_ptr, n_rows * row_bytes);
 
   if (!direct && (rc = ensure_chunks(e, chunk_rows * row_bytes)) != UML_OK) return rc;
   if (e->xchunk_cap < chunk_rows * ld) {
@@ -1153,23 +1202,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   }
   // bytes of one row as it travels: `direct` rows keep their padding up to ld
   const int64_t wire_row_bytes = direct ? ld * 4 : row_bytes;
-  if (bounce) {
-    if (e->bounce_cap < chunk_rows * wire_row_bytes) {
-      for (auto& p : e->h_bounce) {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-      }
-      e->bounce_cap = 0;
-      for (auto& p : e->h_bounce) UML_CUDA(e, cudaHostAlloc(&p, (size_t)(chunk_rows * wire_row_bytes), cudaHostAllocDefault));
-      e->bounce_cap = chunk_rows * wire_row_bytes;
-    }
-    if (!e->pool) {
-      int n = 0;
-      if (const char* env = getenv("UML_B200_COPY_THREADS")) n = atoi(env);
-      if (n <= 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, std::thread::hardware_concurrency() / 4u));
-      e->pool = new CopyPool(n - 1);  // the calling thread is the n-th worker
-    }
-  }
+  if (bounce && (rc = ensure_bounce(e, chunk_rows * wire_row_bytes)) != UML_OK) return rc;
   if (values_out) {
     if (e->vchunk_cap < chunk_rows) {
       for (auto& p : e->d_vchunk) {
@@ -1217,6 +1250,13 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   bool used[3] = {false, false, false};
   int slot = 0;
   std::vector<CopyPool::Task> tasks;
+  // UML_B200_PROFILE_HOST=1: host-side seconds per phase of this call on stderr (diagnostics, not a product feature)
+  static const bool prof = getenv("UML_B200_PROFILE_HOST") != nullptr;
+  double t_wait = 0, t_gather = 0, t_enqueue = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
     const int64_t rows = std::min(chunk_rows, n_rows - r0);
     float* xc = e->d_xchunk[slot];
@@ -1227,7 +1267,10 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     {
       NvtxRange r_h2d("uml:h2d");
       if (bounce) {
+        auto t0 = now();
         if (used[slot]) HOST_CUDA(cudaEventSynchronize(e->chunk_ev[slot]));  // the slot's previous H2D has left the bounce buffer
+        auto t1 = now();
+        t_wait += secs(t0, t1);
         if (direct) {  // already the resident layout (padding included): one contiguous run
           tasks.clear();
           const char* src0 = (const char*)host_ptr + (size_t)r0 * ld * 4;
@@ -1237,8 +1280,12 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
         } else {
           build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F);
         }
+        auto t2 = now();
         e->pool->run(tasks);
+        auto t3 = now();
+        t_gather += secs(t2, t3);
         HOST_CUDA(cudaMemcpyAsync(raw, e->h_bounce[slot], (size_t)(rows * wire_row_bytes), cudaMemcpyHostToDevice, e->copy_stream));
+        t_enqueue += secs(t3, now());
       } else if (direct) {
         HOST_CUDA(cudaMemcpyAsync(xc, (const char*)host_ptr + (size_t)r0 * ld * 4, (size_t)rows * ld * 4,
                                   cudaMemcpyHostToDevice, e->copy_stream));
@@ -1297,6 +1344,10 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   }
   HOST_CUDA(cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
 #undef HOST_CUDA
+  if (prof)
+    fprintf(stderr, "uml predict_host: rows %lld chunk_rows %lld bounce %d direct %d | wait-for-slot %.4f s, gather %.4f s, "
+                    "memcpyAsync enqueue %.4f s\n", (long long)n_rows, (long long)chunk_rows, (int)bounce, (int)direct, t_wait,
+            t_gather, t_enqueue);
   rc = finish_stats(e, stats, n_rows, launches, path, timed, false);
   cudaStreamSynchronize(e->copy_stream);
   if (stats) {
@@ -1411,6 +1462,12 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
 
   uml_mlp* m = new uml_mlp();
   m->e = e;
+  m->host.w1.assign(w1, w1 + (size_t)H * F);
+  m->host.b1.assign(b1, b1 + H);
+  m->host.w2.assign(w2, w2 + (size_t)C * H);
+  m->host.b2.assign(b2, b2 + C);
+  std::vector<float> tiles;
+  if (f_pad <= 128 && (H == 16 || H == 32)) tiles = uml::mlp_tc_build_w1_tiles(w1, H, F, f_pad);
   auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t ce = cudaMalloc(dst, bytes);
     if (ce != cudaSuccess) return ce;
@@ -1421,7 +1478,8 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
       (ce = up((void**)&m->d_b1, b1p.data(), b1p.size() * 4)) != cudaSuccess ||
       (ce = up((void**)&m->d_w2t, w2t.data(), w2t.size() * 4)) != cudaSuccess ||
       (ce = up((void**)&m->d_b2, b2p.data(), b2p.size() * 4)) != cudaSuccess ||
-      (ce = up((void**)&m->d_w64, w64.data(), w64.size() * 8)) != cudaSuccess) {
+      (ce = up((void**)&m->d_w64, w64.data(), w64.size() * 8)) != cudaSuccess ||
+      (!tiles.empty() && (ce = up((void**)&m->d_w1_tiles, tiles.data(), tiles.size() * 4)) != cudaSuccess)) {
     e->last_error = std::string("uml_mlp_load: ") + cudaGetErrorString(ce);
     uml_mlp_free(m);
     return ce == cudaErrorMemoryAllocation ? UML_ERR_NOMEM : UML_ERR_CUDA;
@@ -1440,6 +1498,8 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
   m->dm.cp = cp;
   m->dm.f_pad = f_pad;
   m->dm.w2_abs_row_sum_max = row_sum_max;
+  m->dm.w1_tiles = m->d_w1_tiles;
+  m->dm.host = &m->host;
   *out = m;
   return UML_OK;
 }
@@ -1452,13 +1512,36 @@ void uml_mlp_free(uml_mlp* m) {
   cudaFree(m->d_w2t);
   cudaFree(m->d_b2);
   cudaFree(m->d_w64);
+  cudaFree(m->d_w1_tiles);
   delete m;
 }
 
-int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
-                    int mode, uml_stats* stats) {
-  if (!e || !m || !b || (!labels_out && b->n_rows > 0)) return UML_ERR_INVALID;
+// is every fp32 feature of the batch a tf32 value?  Known from staging; wrapped device rows are scanned once (one
+// HBM pass, cached in the batch handle - the handle is logically const for the caller)
+static int batch_tf32_exact(uml_engine* e, const uml_batch* b) {
+  if (b->tf32_exact >= 0) return b->tf32_exact;
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(e->d_stage, 0, sizeof(StageResult), e->stream)) != cudaSuccess ||
+      (ce = uml::launch_finite_scan(b->x, b->ld, b->n_rows, b->n_features, e->d_stage, e->stream)) != cudaSuccess ||
+      (ce = cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess ||
+      (ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  const_cast<uml_batch*>(b)->tf32_exact = e->h->stage.not_tf32 == 0 ? 1 : 0;
+  return b->tf32_exact;
+}
+
+static int mlp_predict_common(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out,
+                              int labels_on_device, void* const* peers, int n_peers, int64_t row_offset,
+                              int label_bytes, int mode, uml_stats* stats) {
+  if (!e || !m || !b) return UML_ERR_INVALID;
+  if (!labels_out && b->n_rows > 0 && n_peers == 0) return UML_ERR_INVALID;
   if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
+  if (n_peers < 0 || n_peers > 8) UML_FAIL(e, UML_ERR_INVALID, "n_peers %d (max 8)", n_peers);
+  if (n_peers > 0 && label_bytes != 1 && label_bytes != 4) UML_FAIL(e, UML_ERR_INVALID, "label_bytes %d", label_bytes);
+  if (n_peers > 0 && label_bytes == 1 && m->dm.n_classes > 256)
+    UML_FAIL(e, UML_ERR_UNSUPPORTED, "byte labels need n_classes <= 256 (model has %d)", m->dm.n_classes);
   if (b->n_features != m->dm.n_in)
     UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the module is expecting %d features as input.", b->n_features,
              m->dm.n_in);
@@ -1468,46 +1551,107 @@ int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t
   if (b->n_rows == 0) return UML_OK;
   const bool exact = mode == UML_PREDICT_EXACT;
   const bool timed = stats != nullptr;
+  const bool sync_call = stats || (!labels_on_device && labels_out);
   int rc;
   if (exact && (rc = ensure_flags(e, b->n_rows)) != UML_OK) return rc;
+
+  // kernel choice: tensor cores when every feature is a tf32 value (integer / pixel domains), CUDA cores otherwise.
+  // UML_B200_MLP_TC=0 / 1 forces the choice (1: rows that are not tf32-exact are caught in the kernel and re-scored)
+  std::string why;
+  bool use_tc = b->has_map && uml::mlp_tc_supported(m->dm, &why);
+  if (use_tc) {
+    const char* env = getenv("UML_B200_MLP_TC");
+    if (env && env[0] == '0') use_tc = false;
+    else if (!(env && env[0] == '1')) use_tc = batch_tf32_exact(e, b) == 1;
+  }
+  const bool use_ffma = !use_tc && b->has_map && uml::mlp_tma_supported(m->dm, &why);
+
+  uml::MlpTcLaunch out{};
+  out.n_rows = b->n_rows;
+  out.row_offset = row_offset;
+  const bool wire_u8 = n_peers > 0 && label_bytes == 1;
+  out.wire_u8 = wire_u8 ? 1 : 0;
   int32_t* d_labels = labels_out;
-  if (!labels_on_device) {
+  if (n_peers > 0) {
+    out.n_peers = n_peers;
+    for (int i = 0; i < n_peers; ++i) out.peers[i] = peers[i];
+    d_labels = nullptr;
+  } else if (!labels_on_device) {
     if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
     d_labels = e->d_labels;
   }
+  out.labels = d_labels;
+  // the CUDA-core kernel has no peer stores: it writes int32 labels to scratch and a thin kernel scatters them
+  uml::MlpTcLaunch ffma_out = out;
+  if (use_ffma && n_peers > 0) {
+    if ((rc = ensure_labels(e, b->n_rows)) != UML_OK) return rc;
+    ffma_out.labels = e->d_labels;
+  }
+
   FlagList fl{e->d_flag_count, e->d_flag_rows, (int)std::min<int64_t>(e->flag_cap, INT32_MAX), e->d_counters};
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[0], e->stream));
-  UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
-  UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  if (sync_call) {
+    UML_CUDA(e, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), e->stream));
+    UML_CUDA(e, cudaMemsetAsync(e->d_flag_count, 0, sizeof(int), e->stream));
+  }
   int launches = 0, path = 3;
-  std::string why;
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[1], e->stream));
-  if (b->has_map && uml::mlp_tma_supported(m->dm, &why)) {
-    UML_CUDA(e, uml::launch_mlp_tma(b->map, m->dm, b->x, b->n_rows, d_labels, exact, fl, e->info.sm_count, e->stream));
+  if (use_tc) {
+    NvtxRange r_score("uml:mlp_score_tcgen05");
+    UML_CUDA(e, uml::launch_mlp_tc(b->map, m->dm, out, exact, fl, e->info.sm_count, e->stream));
+    launches += 1;
+    path = 5;
+    if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
+    if (exact) {
+      NvtxRange r_rescore("uml:mlp_rescore_f64");
+      UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, out, fl, false, e->info.sm_count, e->stream));
+      launches += 1;
+    }
+  } else if (use_ffma) {
+    NvtxRange r_score("uml:mlp_score_ffma");
+    UML_CUDA(e, uml::launch_mlp_tma(b->map, m->dm, b->x, b->n_rows, ffma_out.labels, exact, fl, e->info.sm_count, e->stream));
     launches += 1;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
     if (exact) {
-      UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, d_labels, fl, false, e->info.sm_count, e->stream));
+      UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, ffma_out, fl, false, e->info.sm_count, e->stream));
+      launches += 1;
+    }
+    if (n_peers > 0) {
+      UML_CUDA(e, uml::launch_labels_scatter(e->d_labels, b->n_rows, out.peers, n_peers, out.wire_u8, row_offset,
+                                             e->info.sm_count, e->stream));
       launches += 1;
     }
   } else {
-    UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, d_labels, fl, true, e->info.sm_count, e->stream));
+    NvtxRange r_score("uml:mlp_score_f64_generic");
+    UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, out, fl, true, e->info.sm_count, e->stream));
     launches += 1;
     path = 2;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
   }
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[3], e->stream));
   int64_t d2h = 0;
-  if (!labels_on_device) {
+  if (!labels_on_device && labels_out) {
     UML_CUDA(e, cudaMemcpyAsync(labels_out, d_labels, (size_t)b->n_rows * 4, cudaMemcpyDeviceToHost, e->stream));
     d2h = b->n_rows * 4;
   }
-  if (stats || !labels_on_device) {
+  if (sync_call) {
     rc = finish_stats(e, stats, b->n_rows, launches, path, timed);
     if (stats) stats->d2h_bytes = d2h;
     return rc;
   }
   return UML_OK;
+}
+
+int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
+                    int mode, uml_stats* stats) {
+  if (b && !labels_out && b->n_rows > 0) return UML_ERR_INVALID;
+  return mlp_predict_common(e, m, b, labels_out, labels_on_device, nullptr, 0, 0, 4, mode, stats);
+}
+
+int uml_mlp_predict_peers(uml_engine* e, const uml_mlp* m, const uml_batch* b, void* const* peer_labels, int n_peers,
+                          int64_t row_offset, int label_bytes, int mode, uml_stats* stats) {
+  if (!peer_labels || n_peers < 1) return UML_ERR_INVALID;
+  return mlp_predict_common(e, m, b, nullptr, 1, peer_labels, n_peers, row_offset, label_bytes, mode, stats);
 }
 
 }  // extern "C"

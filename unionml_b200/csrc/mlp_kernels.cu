@@ -12,7 +12,8 @@
 //    shapes the tile kernel is not instantiated for.
 //
 // This is CUDA-core fp32 (FFMA): 4 736 flop/row puts the HBM roofline (25 G rows/s) above the FFMA peak, so this kernel
-// is FMA-pipe bound (~0.66 ms per 10M rows at 1.9 GHz); a tcgen05 TF32x3 layer 1 is the planned next step.
+// is FMA-pipe bound (~0.66 ms per 10M rows at 1.9 GHz).  It serves batches whose features are NOT tf32 values (general
+// floats); tf32-representable batches (integer / pixel domains) take the tensor-core kernel in mlp_tc_kernels.cu.
 #include <algorithm>
 #include <cstdlib>
 
@@ -276,6 +277,10 @@ struct MlpRescoreParams {
   int flag_cap;
   int all_rows;
   int32_t* labels;
+  void* peers[8];
+  int n_peers;
+  int wire_u8;
+  long long row_offset;
   unsigned long long* counters;
 };
 
@@ -338,10 +343,25 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
       }
     }
     if (lane == 0) {
-      p.labels[row] = idx;
+      if (p.labels) p.labels[row] = idx;
+      for (int q = 0; q < p.n_peers; ++q) {
+        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(idx);
+        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
+      }
       if (bad) atomicAdd(&p.counters[1], 1ull);
       const double err = (static_cast<double>(p.F + p.H) + 16.0) * u * amax;
       if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
+    }
+  }
+  // hand the flag list back empty (see rescore_f64_kernel in linear_kernels.cu)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&p.counters[3], 1ull);
+    if (ticket == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+      *const_cast<int*>(p.flag_count) = 0;
+      p.counters[3] = 0ull;
+      __threadfence();
     }
   }
 }
@@ -371,8 +391,12 @@ template <int H, int C, bool EXACT>
 static cudaError_t mlp_launch_one(const CUtensorMap& xmap, const MlpKernelParams& p, int grid, size_t smem,
                                   cudaStream_t stream) {
   auto kern = mlp_argmax_tma_kernel<H, C, EXACT>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
   kern<<<grid, kMlpThreads, smem, stream>>>(xmap, p);
   return cudaGetLastError();
 }
@@ -420,8 +444,9 @@ cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, con
                : mlp_dispatch<false>(m.n_hidden, m.n_classes, xmap, p, grid, smem, stream);
 }
 
-cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, int32_t* labels,
-                                   const FlagList& flags, bool all_rows, int sm_count, cudaStream_t stream) {
+cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows,
+                                   const MlpTcLaunch& out, const FlagList& flags, bool all_rows, int sm_count,
+                                   cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   MlpRescoreParams p{};
   p.x = x;
@@ -438,7 +463,11 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   p.flag_rows = flags.rows;
   p.flag_cap = flags.capacity;
   p.all_rows = all_rows ? 1 : 0;
-  p.labels = labels;
+  p.labels = out.labels;
+  p.n_peers = out.n_peers;
+  p.wire_u8 = out.wire_u8;
+  for (int i = 0; i < 8; ++i) p.peers[i] = i < out.n_peers ? out.peers[i] : nullptr;
+  p.row_offset = out.row_offset;
   p.counters = flags.counters;
   long long blocks = static_cast<long long>(sm_count) * 8;
   if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 7) / 8);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/uml_b200.h"
 
@@ -87,7 +88,10 @@ cudaError_t launch_linear_small(const LinearDeviceModel& m, const SrcView& src, 
 cudaError_t launch_linear_proba(const LinearDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, float* proba,
                                 int sm_count, cudaStream_t stream);
 
-// 2-layer MLP (mlp_kernels.cu)
+// 2-layer MLP (mlp_kernels.cu, mlp_tc_kernels.cu)
+struct MlpHostModel {  // the caller's fp32 weights, torch nn.Linear layout
+  std::vector<float> w1, b1, w2, b2;  // w1 [H][F], b1 [H], w2 [C][H], b2 [C]
+};
 struct MlpDeviceModel {
   const float* w1t;  // [f_pad][H + 4], column H = max_n |w1_nf|
   const float* b1;   // [H + 4], entry H = max_n |b1_n|
@@ -100,17 +104,38 @@ struct MlpDeviceModel {
   int n_in, n_hidden, n_classes;
   int cp, f_pad;
   double w2_abs_row_sum_max;  // max_c sum_n |w2_cn|
+  // tensor-core kernel: W1 split into tf32 hi | lo rows, pre-swizzled per 32-feature chunk (nullptr: not built)
+  const float* w1_tiles;
+  const MlpHostModel* host;
+};
+// where the labels of an MLP launch go (same contract as LinearLaunch's label fields)
+struct MlpTcLaunch {
+  int32_t* labels;  // local int32 vector or nullptr
+  void* peers[8];
+  int n_peers;
+  int wire_u8;
+  long long row_offset;
+  long long n_rows;
 };
 bool mlp_tma_supported(const MlpDeviceModel& m, std::string* why);
 cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, const float* x, int64_t n_rows,
                            int32_t* labels, bool exact, const FlagList& flags, int sm_count, cudaStream_t stream);
-cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows, int32_t* labels,
-                                   const FlagList& flags, bool all_rows, int sm_count, cudaStream_t stream);
+cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int64_t ld, int64_t n_rows,
+                                   const MlpTcLaunch& out, const FlagList& flags, bool all_rows, int sm_count,
+                                   cudaStream_t stream);
+bool mlp_tc_supported(const MlpDeviceModel& m, std::string* why);
+std::vector<float> mlp_tc_build_w1_tiles(const float* w1, int H, int F, int f_pad);
+cudaError_t launch_mlp_tc(const CUtensorMap& xmap, const MlpDeviceModel& m, const MlpTcLaunch& l, bool exact,
+                          const FlagList& flags, int sm_count, cudaStream_t stream);
+// int32 labels (device) -> every target vector of a fused exchange (int32 or uint8 wire), for kernels without peer stores
+cudaError_t launch_labels_scatter(const int32_t* labels, int64_t n, void* const* peers, int n_peers, int wire_u8,
+                                  int64_t row_offset, int sm_count, cudaStream_t stream);
 
 // staging kernels (stage_kernels.cu)
 struct StageResult {  // device-side counters
   unsigned long long nonfinite;
   unsigned long long lossy;
+  unsigned long long not_tf32;  // fp32 values with any of the low 13 mantissa bits set (tensor-core path needs none)
 };
 cudaError_t launch_stage_convert(const void* src, int src_dtype, bool feature_major, int64_t src_pitch_elems,
                                  int64_t rows, int n_features, float* dst, int64_t ld, double* dst64, int64_t ld64,

@@ -210,6 +210,10 @@ class Dataset:
         wanted = self._features
         if not wanted and self._targets is not None:
             wanted = [c for c in frame.columns if c not in self._targets]
+        if wanted is not None and len(wanted) == frame.shape[1] and list(wanted) == list(frame.columns):
+            # the selection is the identity (same columns, same order): hand the frame through instead of letting
+            # `frame[wanted]` copy every block - a 10M x 64 float64 frame is 5 GB (SURVEY.md 8a row a2 "where time goes")
+            return frame
         return frame[wanted]
 
     def _default_feature_transformer(self, features: Any) -> Any:

@@ -269,6 +269,19 @@ class Engine:
             self._check(st)  # under the lock: uml_last_error is per engine, another thread's call may overwrite it
         return out, stats.as_dict() if stats else None
 
+    def predict_mlp_peers(self, model: MlpModel, batch: Batch, peer_ptrs, row_offset: int, exact: bool = True,
+                          want_stats: bool = False, label_bytes: int = 4) -> Optional[dict]:
+        """Fused compute + all-gather for the MLP predictor (same contract as :meth:`predict_peers`)."""
+        mode = N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
+        stats = N.Stats() if want_stats else None
+        with self._lock:
+            st = N.lib().uml_mlp_predict_peers(
+                self._h, model._h, batch._h, arr, len(peer_ptrs), row_offset, label_bytes, mode, C.byref(stats) if stats else None
+            )
+            self._check(st)
+        return stats.as_dict() if stats else None
+
     def stage(self, features: Any, keep_f64: bool = True, check_finite: bool = True) -> Batch:
         """Host rows (ndarray / DataFrame, any order, f32/f64/int) -> device fp32 row-major, converted on the GPU."""
         arr = as_feature_array(features)
