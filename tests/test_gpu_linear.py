@@ -60,7 +60,7 @@ def test_committed_fixture(engine, digits_model, synthetic_digits):
         b = engine.stage(arr)
         idx2, st2 = engine.predict(m, b, exact=True)
         np.testing.assert_array_equal(idx2, idx)
-        assert st2["path"] == 1 and st2["kernel_launches"] == 2
+        assert st2["path"] == 1 and st2["kernel_launches"] == 1  # flagged rows are re-scored inside the tile kernel
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -135,6 +135,32 @@ def test_layouts_and_dtypes(engine, digits_model):
         np.testing.assert_array_equal(got, w, err_msg=name)
         got2, _ = engine.predict(m, engine.stage(arr), exact=True)
         np.testing.assert_array_equal(got2, w, err_msg=name)
+
+
+def test_inline_and_list_rescore_agree(engine, digits_model):
+    """UML_B200_INLINE_RESCORE=0 keeps the round-1 scheme (flag list + rescore_f64_kernel); same labels, same counters."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from unionml_b200.engine import Engine\n"
+        "z = np.load(%r); e = Engine(0); m = e.load_linear(z['coef'], z['intercept'])\n"
+        "X = np.random.default_rng(31).integers(0, 17, size=(1_500_000, 64), dtype=np.uint8).astype(np.float32)\n"
+        "idx, st = e.predict(m, e.stage(X), exact=True)\n"
+        "print(st['kernel_launches'], st['n_flagged'], int(idx.astype(np.int64).sum()), int((idx * np.arange(idx.size) %% 1000003).sum()))\n"
+    ) % (str(root), str(root / "tests" / "golden" / "digits_lr.npz"))
+    outs = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, UML_B200_INLINE_RESCORE=flag)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.split())
+    assert outs[0][0] == "1" and outs[1][0] == "2"   # one launch inline, two with the flag list
+    assert outs[0][1:] == outs[1][1:] and int(outs[0][1]) > 0
 
 
 def test_lossy_float64_features_use_the_f64_copy(engine):

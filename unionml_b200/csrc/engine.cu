@@ -170,6 +170,8 @@ struct uml_engine {
   int classes_cap = 0;
   void* h_bounce[3] = {nullptr, nullptr, nullptr};  // pinned bounce buffers for pageable sources
   int64_t bounce_cap = 0;
+  void* h_result[3] = {nullptr, nullptr, nullptr};  // pinned landing slots for labels / values bound for pageable outputs
+  int64_t result_cap = 0;
   CopyPool* pool = nullptr;
   // online path (B <= kSmallRows): pinned request buffer, its device twin, result slots, cached graphs
   void* h_req = nullptr;
@@ -335,6 +337,8 @@ void uml_engine_destroy(uml_engine* e) {
   for (auto p : e->d_vchunk) cudaFree(p);
   cudaFree(e->d_classes);
   for (auto p : e->h_bounce)
+    if (p) cudaFreeHost(p);
+  for (auto p : e->h_result)
     if (p) cudaFreeHost(p);
   delete e->pool;
   for (auto& g : e->small_graphs)
@@ -840,12 +844,13 @@ static int enqueue_predict(uml_engine* e, const uml_model* m, const LinearLaunch
   if (tma) {
     NvtxRange r_score("uml:score");
     std::string err;
-    cudaError_t ce = uml::launch_linear_tma(*map, m->dm, l, exact, fl, e->info.sm_count, e->stream, &err);
+    bool need_rescore = false;
+    cudaError_t ce = uml::launch_linear_tma(*map, m->dm, l, exact, fl, e->info.sm_count, e->stream, &err, &need_rescore);
     if (ce != cudaSuccess) UML_FAIL(e, UML_ERR_CUDA, "linear_argmax_tma launch: %s %s", cudaGetErrorString(ce), err.c_str());
     *launches += 1;
     *path = 1;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
-    if (exact) {
+    if (need_rescore) {  // only with UML_B200_INLINE_RESCORE=0: flagged rows are otherwise re-scored inside the tile kernel
       NvtxRange r_rescore("uml:rescore_f64");
       UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, false, e->info.sm_count, e->stream));
       *launches += 1;
@@ -1223,6 +1228,33 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   }
   if ((rc = ensure_labels(e, 3 * chunk_rows)) != UML_OK) return rc;
   if (exact && (rc = ensure_flags(e, chunk_rows)) != UML_OK) return rc;
+  // A device-to-host copy into PAGEABLE memory blocks the calling thread until the chunk's whole pipeline has drained,
+  // which would serialise gather / H2D / scoring.  Pageable outputs therefore land in pinned slots first and are
+  // copied out by the host when the slot comes round again (three chunks later) or at the end.
+  const bool result_bounce = (labels_out && !host_ptr_is_pinned(labels_out)) || (values_out && !host_ptr_is_pinned(values_out));
+  if (result_bounce && e->result_cap < chunk_rows * 12) {
+    for (auto& p : e->h_result) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+    }
+    e->result_cap = 0;
+    for (auto& p : e->h_result) UML_CUDA(e, cudaHostAlloc(&p, (size_t)(chunk_rows * 12), cudaHostAllocDefault));
+    e->result_cap = chunk_rows * 12;
+  }
+  struct Pending {
+    int64_t r0 = 0, rows = 0;
+    bool live = false;
+  } pending[3];
+  auto flush_slot = [&](int sl) -> cudaError_t {
+    if (!pending[sl].live) return cudaSuccess;
+    cudaError_t fe = cudaEventSynchronize(e->chunk_ev[3 + sl]);  // recorded after the slot's D2H copies
+    if (fe != cudaSuccess) return fe;
+    const char* base = (const char*)e->h_result[sl];
+    if (values_out) memcpy(values_out + pending[sl].r0, base, (size_t)pending[sl].rows * 8);
+    if (labels_out) memcpy(labels_out + pending[sl].r0, base + (size_t)chunk_rows * 8, (size_t)pending[sl].rows * 4);
+    pending[sl].live = false;
+    return cudaSuccess;
+  };
 
   const bool timed = stats != nullptr;
   cudaStream_t cs = e->stream;
@@ -1257,13 +1289,24 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double>(b - a).count();
   };
+  // ... and, for the first chunks, a device timeline from CUDA events on both streams (H2D / convert+score+D2H), which
+  // is what shows the overlap of the pipeline without nsys
+  constexpr int kTl = 12;
+  cudaEvent_t tl[kTl][4] = {};
+  int tl_n = 0;
+  if (prof)
+    for (auto& row : tl)
+      for (auto& ev : row) cudaEventCreate(&ev);
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows, slot = (slot + 1) % 3) {
     const int64_t rows = std::min(chunk_rows, n_rows - r0);
     float* xc = e->d_xchunk[slot];
     void* raw = direct ? (void*)xc : e->d_chunk[slot];
+    const int tli = (prof && tl_n < kTl) ? tl_n++ : -1;
     // (1) H2D on the copy stream, once the previous user of this slot has finished scoring (the re-score reads the
     //     raw chunk, so that includes it)
     if (used[slot]) HOST_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));
+    if (result_bounce) HOST_CUDA(flush_slot(slot));
+    if (tli >= 0) cudaEventRecord(tl[tli][0], e->copy_stream);
     {
       NvtxRange r_h2d("uml:h2d");
       if (bounce) {
@@ -1294,8 +1337,10 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
       }
     }
     h2d += rows * wire_row_bytes;
+    if (tli >= 0) cudaEventRecord(tl[tli][1], e->copy_stream);
     HOST_CUDA(cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
     HOST_CUDA(cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
+    if (tli >= 0) cudaEventRecord(tl[tli][2], cs);
     // (2) transpose / down-cast (+ finiteness) on the compute stream
     if (!direct) {
       NvtxRange r_stage("uml:stage_convert");
@@ -1329,27 +1374,56 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
       return rc;
     }
     // (4) labels (or class values) back
+    char* land = result_bounce ? (char*)e->h_result[slot] : nullptr;
     if (values_out) {
       HOST_CUDA(uml::launch_labels_take(l.labels, 4, rows, e->d_classes, n_classes, e->d_vchunk[slot], cs));
       launches += 1;
-      HOST_CUDA(cudaMemcpyAsync(values_out + r0, e->d_vchunk[slot], (size_t)rows * 8, cudaMemcpyDeviceToHost, cs));
+      HOST_CUDA(cudaMemcpyAsync(land ? (void*)land : (void*)(values_out + r0), e->d_vchunk[slot], (size_t)rows * 8,
+                                cudaMemcpyDeviceToHost, cs));
       d2h += rows * 8;
     }
     if (labels_out) {
-      HOST_CUDA(cudaMemcpyAsync(labels_out + r0, l.labels, (size_t)rows * 4, cudaMemcpyDeviceToHost, cs));
+      HOST_CUDA(cudaMemcpyAsync(land ? (void*)(land + (size_t)chunk_rows * 8) : (void*)(labels_out + r0), l.labels,
+                                (size_t)rows * 4, cudaMemcpyDeviceToHost, cs));
       d2h += rows * 4;
     }
+    if (result_bounce) {
+      pending[slot].r0 = r0;
+      pending[slot].rows = rows;
+      pending[slot].live = true;
+    }
+    if (tli >= 0) cudaEventRecord(tl[tli][3], cs);
     HOST_CUDA(cudaEventRecord(e->chunk_ev[3 + slot], cs));
     used[slot] = true;
   }
   HOST_CUDA(cudaMemcpyAsync(&e->h->stage, e->d_stage, sizeof(StageResult), cudaMemcpyDeviceToHost, cs));
 #undef HOST_CUDA
+  if (prof && tl_n > 0) {
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(e->copy_stream);
+    fprintf(stderr, "uml predict_host timeline (ms since the first H2D began; chunk: h2d [begin,end]  convert+score+d2h [begin,end])\n");
+    for (int i = 0; i < tl_n; ++i) {
+      float a = 0, b2 = 0, c = 0, d = 0;
+      cudaEventElapsedTime(&a, tl[0][0], tl[i][0]);
+      cudaEventElapsedTime(&b2, tl[0][0], tl[i][1]);
+      cudaEventElapsedTime(&c, tl[0][0], tl[i][2]);
+      cudaEventElapsedTime(&d, tl[0][0], tl[i][3]);
+      fprintf(stderr, "  chunk %2d: h2d [%7.3f, %7.3f]  compute [%7.3f, %7.3f]\n", i, a, b2, c, d);
+    }
+    (void)cudaGetLastError();
+  }
+  if (prof)
+    for (auto& row : tl)
+      for (auto& ev : row)
+        if (ev) cudaEventDestroy(ev);
   if (prof)
     fprintf(stderr, "uml predict_host: rows %lld chunk_rows %lld bounce %d direct %d | wait-for-slot %.4f s, gather %.4f s, "
                     "memcpyAsync enqueue %.4f s\n", (long long)n_rows, (long long)chunk_rows, (int)bounce, (int)direct, t_wait,
             t_gather, t_enqueue);
   rc = finish_stats(e, stats, n_rows, launches, path, timed, false);
   cudaStreamSynchronize(e->copy_stream);
+  for (int sl = 0; sl < 3; ++sl)
+    if (flush_slot(sl) != cudaSuccess && rc == UML_OK) rc = UML_ERR_CUDA;
   if (stats) {
     stats->h2d_bytes = h2d;
     stats->d2h_bytes = d2h;
@@ -1455,7 +1529,9 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
   b2p[C] = bmax;
   std::vector<double> w64((size_t)H * F + H + (size_t)C * H + C);
   double* q = w64.data();
-  for (size_t i = 0; i < (size_t)H * F; ++i) *q++ = w1[i];
+  // W1 feature-major [F][H] for the fp64 re-score: lane n reads w1t[f][n], consecutive doubles across the warp
+  for (int f = 0; f < F; ++f)
+    for (int n = 0; n < H; ++n) *q++ = w1[(size_t)n * F + f];
   for (int i = 0; i < H; ++i) *q++ = b1[i];
   for (size_t i = 0; i < (size_t)C * H; ++i) *q++ = w2[i];
   for (int i = 0; i < C; ++i) *q++ = b2[i];

@@ -22,6 +22,65 @@
 
 namespace uml {
 
+// one element of the caller's raw source chunk as float64 (exact for every dtype the ABI takes)
+__device__ __forceinline__ double load_src(const SrcView& v, long long row, int f) {
+  const long long i = row * v.row_stride + static_cast<long long>(f) * v.col_stride;
+  switch (v.dtype) {
+    case UML_F64: return static_cast<const double*>(v.base)[i];
+    case UML_I64: return static_cast<double>(static_cast<const long long*>(v.base)[i]);
+    case UML_I32: return static_cast<double>(static_cast<const int*>(v.base)[i]);
+    case UML_U8: return static_cast<double>(static_cast<const unsigned char*>(v.base)[i]);
+    default: return static_cast<double>(static_cast<const float*>(v.base)[i]);
+  }
+}
+
+struct RowScore {
+  int idx;
+  bool bad;        // NaN/Inf in the row
+  bool ambiguous;  // fp64 top-2 margin inside the fp64 rounding bound: a true tie, decided by the first-index rule
+};
+
+// float64 scores of one row by one warp (lanes over features, butterfly sums), first maximum wins like np.argmax.
+// LOAD(f) yields feature f of the row as double.
+template <typename LOAD>
+__device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, const double* __restrict__ b64,
+                                                  int F, int C, int lane) {
+  const double u = 1.1102230246251565e-16;  // 2^-53
+  bool bad = false;
+  double best = 0.0, second = -INFINITY, amax = 0.0;
+  int idx = 0;
+  for (int c = 0; c < C; ++c) {
+    const double* wc = w64 + static_cast<long long>(c) * F;
+    double s = 0.0, a = 0.0;
+    for (int f = lane; f < F; f += 32) {
+      const double xv = load(f);
+      if (c == 0 && !isfinite(xv)) bad = true;
+      const double w = wc[f];
+      s = fma(xv, w, s);
+      a = fma(fabs(xv), fabs(w), a);
+    }
+    s = warp_sum(s) + b64[c];
+    a = warp_sum(a) + fabs(b64[c]);
+    amax = fmax(amax, a);
+    if (c == 0) {
+      best = s;
+    } else if (s > best) {
+      second = best;
+      best = s;
+      idx = c;
+    } else {
+      second = fmax(second, s);
+    }
+  }
+  RowScore r;
+  r.idx = idx;
+  r.bad = __any_sync(0xffffffffu, bad);
+  // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
+  const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
+  r.ambiguous = !((best - second) > 2.0 * err);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // TMA fp32 tile kernel
 // ---------------------------------------------------------------------------------------------------------------
@@ -42,11 +101,41 @@ struct TmaKernelParams {
   int* flag_count;
   int32_t* flag_rows;
   int flag_cap;
+  // INLINE re-score (EXACT kernels): a flagged row is re-scored in fp64 by its own warp right in the epilogue - no flag
+  // list, no second kernel launch behind every step
+  const float* x;
+  const double* x64;
+  SrcView src;
+  long long ld, ld64;
+  const double* w64;
+  const double* b64;
+  int n_classes, n_features;
+  unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] re-scored rows
 };
 
-template <int C, bool EXACT>
+// fp64 scores of one row by the whole warp (kept out of line so the hot loop's register allocation is untouched)
+__device__ __noinline__ int rescore_row_inline(const TmaKernelParams& p, long long row, int lane) {
+  RowScore r;
+  if (p.src.base) {
+    const SrcView v = p.src;
+    r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+  } else if (p.x64) {
+    const double* xr64 = p.x64 + row * p.ld64;
+    r = score_row_f64([&](int f) { return xr64[f]; }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+  } else {
+    const float* xr = p.x + row * p.ld;
+    r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+  }
+  if (lane == 0) {
+    if (r.bad) atomicAdd(&p.counters[1], 1ull);
+    if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
+  }
+  return r.idx;
+}
+
+template <int C, bool EXACT, bool INLINE>
 __global__ void __launch_bounds__(kThreads, 1)
-linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKernelParams p) {
+linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TmaKernelParams p) {
   constexpr int NCOL = C + (EXACT ? 1 : 0);  // accumulators per row (classes + error-bound column)
   constexpr int CP = (C + 1 + 3) / 4 * 4;    // padded columns of wt in shared memory (layout shared by both modes)
   constexpr int NW4 = (NCOL + 3) / 4;        // float4 loads of W per feature
@@ -209,6 +298,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
         // ---- fused epilogue: argmax (first maximum wins), margin guard, label store (+ peer stores) ----
         const long long row0 = tile * kTileRows;
         int idxs[R];
+        bool flag[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const long long row = row0 + lane + 32 * j;
@@ -227,22 +317,40 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const TmaKern
             }
           }
           idxs[j] = idx;
-          const bool in_range = row < p.n_rows;
-          if (in_range) {
-            if (p.labels) p.labels[row] = idx;
-            if (!p.wire_u8)
-              for (int i = 0; i < p.n_peers; ++i) static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idx;
+          // certain iff margin > 2 * err, err <= (F+4) 2^-24 A; NaN/Inf anywhere makes the comparison false
+          flag[j] = EXACT && row < p.n_rows && !((best - second) > p.thr * acc[j][C]);
+        }
+        if constexpr (EXACT && INLINE) {
+          // re-score the (rare) flagged rows now, warp-wide in fp64, so the labels below are final
+          int n_flag = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            unsigned mask = __ballot_sync(0xffffffffu, flag[j]);
+            n_flag += __popc(mask);
+            while (mask != 0u) {
+              const int l = __ffs(static_cast<int>(mask)) - 1;
+              mask &= mask - 1u;
+              const int idx64 = rescore_row_inline(p, row0 + l + 32 * j, lane);
+              if (lane == l) idxs[j] = idx64;
+            }
           }
-          if (EXACT) {
-            // certain iff margin > 2 * err, err <= (F+4) 2^-24 A; NaN/Inf anywhere makes the comparison false
-            const bool certain = (best - second) > p.thr * acc[j][C];
-            const bool flagged = in_range && !certain;
-            const unsigned mask = __ballot_sync(0xffffffffu, flagged);
+          if (lane == 0 && n_flag > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n_flag));
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const long long row = row0 + lane + 32 * j;
+          if (row < p.n_rows) {
+            if (p.labels) p.labels[row] = idxs[j];
+            if (!p.wire_u8)
+              for (int i = 0; i < p.n_peers; ++i) static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idxs[j];
+          }
+          if constexpr (EXACT && !INLINE) {
+            const unsigned mask = __ballot_sync(0xffffffffu, flag[j]);
             if (mask != 0u) {
               int base = 0;
               if (lane == 0) base = atomicAdd(p.flag_count, __popc(mask));
               base = __shfl_sync(0xffffffffu, base, 0);
-              if (flagged) {
+              if (flag[j]) {
                 const int pos = base + __popc(mask & ((1u << lane) - 1u));
                 if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
               }
@@ -302,65 +410,6 @@ struct RescoreParams {
   unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] flagged (re-scored) rows
 };
 
-
-// one element of the caller's raw source chunk as float64 (exact for every dtype the ABI takes)
-__device__ __forceinline__ double load_src(const SrcView& v, long long row, int f) {
-  const long long i = row * v.row_stride + static_cast<long long>(f) * v.col_stride;
-  switch (v.dtype) {
-    case UML_F64: return static_cast<const double*>(v.base)[i];
-    case UML_I64: return static_cast<double>(static_cast<const long long*>(v.base)[i]);
-    case UML_I32: return static_cast<double>(static_cast<const int*>(v.base)[i]);
-    case UML_U8: return static_cast<double>(static_cast<const unsigned char*>(v.base)[i]);
-    default: return static_cast<double>(static_cast<const float*>(v.base)[i]);
-  }
-}
-
-struct RowScore {
-  int idx;
-  bool bad;        // NaN/Inf in the row
-  bool ambiguous;  // fp64 top-2 margin inside the fp64 rounding bound: a true tie, decided by the first-index rule
-};
-
-// float64 scores of one row by one warp (lanes over features, butterfly sums), first maximum wins like np.argmax.
-// LOAD(f) yields feature f of the row as double.
-template <typename LOAD>
-__device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, const double* __restrict__ b64,
-                                                  int F, int C, int lane) {
-  const double u = 1.1102230246251565e-16;  // 2^-53
-  bool bad = false;
-  double best = 0.0, second = -INFINITY, amax = 0.0;
-  int idx = 0;
-  for (int c = 0; c < C; ++c) {
-    const double* wc = w64 + static_cast<long long>(c) * F;
-    double s = 0.0, a = 0.0;
-    for (int f = lane; f < F; f += 32) {
-      const double xv = load(f);
-      if (c == 0 && !isfinite(xv)) bad = true;
-      const double w = wc[f];
-      s = fma(xv, w, s);
-      a = fma(fabs(xv), fabs(w), a);
-    }
-    s = warp_sum(s) + b64[c];
-    a = warp_sum(a) + fabs(b64[c]);
-    amax = fmax(amax, a);
-    if (c == 0) {
-      best = s;
-    } else if (s > best) {
-      second = best;
-      best = s;
-      idx = c;
-    } else {
-      second = fmax(second, s);
-    }
-  }
-  RowScore r;
-  r.idx = idx;
-  r.bad = __any_sync(0xffffffffu, bad);
-  // fp64 error of each score <= (F/32 + 7) u a  (<= 32-way split FMA chains + 5 shuffle adds + bias add)
-  const double err = (static_cast<double>(F) / 32.0 + 8.0) * u * amax;
-  r.ambiguous = !((best - second) > 2.0 * err);
-  return r;
-}
 
 __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
   const int lane = threadIdx.x & 31;
@@ -573,10 +622,10 @@ bool linear_tma_supported(const LinearDeviceModel& m, std::string* why) {
   return true;
 }
 
-template <int C, bool EXACT>
+template <int C, bool EXACT, bool INLINE>
 static cudaError_t launch_one(const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
                               cudaStream_t stream) {
-  auto kern = linear_argmax_tma_kernel<C, EXACT>;
+  auto kern = linear_argmax_tma_kernel<C, EXACT, INLINE>;
   static size_t configured = 0;  // per instantiation (one device per process): set the attribute once, not per launch
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -587,13 +636,13 @@ static cudaError_t launch_one(const CUtensorMap& xmap, const TmaKernelParams& p,
   return cudaGetLastError();
 }
 
-template <bool EXACT>
+template <bool EXACT, bool INLINE>
 static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
                                     cudaStream_t stream) {
   switch (C) {
 #define UML_CASE(N) \
   case N:           \
-    return launch_one<N, EXACT>(xmap, p, grid, smem, stream);
+    return launch_one<N, EXACT, INLINE>(xmap, p, grid, smem, stream);
     UML_CASE(2) UML_CASE(3) UML_CASE(4) UML_CASE(5) UML_CASE(6) UML_CASE(7) UML_CASE(8) UML_CASE(9) UML_CASE(10)
     UML_CASE(11) UML_CASE(12) UML_CASE(13) UML_CASE(14) UML_CASE(15) UML_CASE(16)
 #undef UML_CASE
@@ -602,8 +651,17 @@ static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKer
   }
 }
 
+bool linear_inline_rescore_default() {
+  // UML_B200_INLINE_RESCORE=0 keeps the round-1 scheme (flag list + rescore_f64_kernel) for A/B runs
+  static const bool on = !(getenv("UML_B200_INLINE_RESCORE") && getenv("UML_B200_INLINE_RESCORE")[0] == '0');
+  return on;
+}
+
 cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
-                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err) {
+                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err,
+                              bool* rescore_kernel_needed) {
+  const bool inline_rescore = exact && linear_inline_rescore_default();
+  if (rescore_kernel_needed) *rescore_kernel_needed = exact && !inline_rescore;
   if (!linear_tma_supported(m, err)) return cudaErrorInvalidValue;
   if (l.n_rows <= 0) return cudaSuccess;
   TmaKernelParams p{};
@@ -630,11 +688,22 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
   p.flag_count = flags.count;
   p.flag_rows = flags.rows;
   p.flag_cap = flags.capacity;
+  p.x = l.x;
+  p.x64 = l.x64;
+  p.src = l.src;
+  p.ld = l.ld;
+  p.ld64 = l.ld64;
+  p.w64 = m.w64;
+  p.b64 = m.b64;
+  p.n_classes = m.n_classes;
+  p.n_features = m.n_features;
+  p.counters = flags.counters;
   const size_t smem = fixed + static_cast<size_t>(stages) * kStageBytes;
   const long long slots = (p.num_tiles + kConsumerWarps - 1) / kConsumerWarps;
   const int grid = static_cast<int>(std::min<long long>(sm_count, std::max<long long>(1, slots)));
-  return exact ? dispatch_classes<true>(m.n_classes, xmap, p, grid, smem, stream)
-               : dispatch_classes<false>(m.n_classes, xmap, p, grid, smem, stream);
+  if (!exact) return dispatch_classes<false, false>(m.n_classes, xmap, p, grid, smem, stream);
+  return inline_rescore ? dispatch_classes<true, true>(m.n_classes, xmap, p, grid, smem, stream)
+                        : dispatch_classes<true, false>(m.n_classes, xmap, p, grid, smem, stream);
 }
 
 cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,

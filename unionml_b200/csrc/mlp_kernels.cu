@@ -267,7 +267,7 @@ struct MlpRescoreParams {
   const float* x;
   long long ld;
   long long n_rows;
-  const double* w1;  // [H][F]
+  const double* w1;  // [F][H]
   const double* b1;
   const double* w2;  // [C][H]
   const double* b2;
@@ -305,12 +305,14 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
       hval[t] = 0.0;
       herr[t] = 0.0;
       if (hn < p.H) {
-        const double* w1n = p.w1 + static_cast<long long>(hn) * p.F;
+        const double* w1n = p.w1 + hn;  // w1 is [F][H]: the warp's 32 hidden units read 256 contiguous bytes per feature
         double hsum = p.b1[hn], habs = fabs(p.b1[hn]);
+#pragma unroll 8
         for (int f = 0; f < p.F; ++f) {
           const double xv = static_cast<double>(xr[f]);
-          hsum = fma(xv, w1n[f], hsum);
-          habs = fma(fabs(xv), fabs(w1n[f]), habs);
+          const double w = w1n[static_cast<long long>(f) * p.H];
+          hsum = fma(xv, w, hsum);
+          habs = fma(fabs(xv), fabs(w), habs);
         }
         hval[t] = fmax(hsum, 0.0);
         herr[t] = (p.F + 2.0) * u * habs;  // the hidden unit's own fp64 rounding error

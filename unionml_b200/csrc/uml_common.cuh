@@ -71,8 +71,10 @@ struct LinearLaunch {
 };
 
 // scoring kernels (linear_kernels.cu)
+// *rescore_kernel_needed: exact mode with the inline re-score switched off -> the caller launches launch_rescore_f64
 cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
-                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err);
+                              const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err,
+                              bool* rescore_kernel_needed);
 bool linear_tma_supported(const LinearDeviceModel& m, std::string* why);
 cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l, const FlagList& flags, bool all_rows,
                                int sm_count, cudaStream_t stream);
@@ -97,7 +99,7 @@ struct MlpDeviceModel {
   const float* b1;   // [H + 4], entry H = max_n |b1_n|
   const float* w2t;  // [H][cp], column C = max_c |w2_cn|
   const float* b2;   // [cp], entry C = max_c |b2_c|
-  const double* w1_64;  // [H][F]
+  const double* w1_64;  // [F][H] feature-major (coalesced across the warp's hidden units in the re-score kernel)
   const double* b1_64;
   const double* w2_64;  // [C][H]
   const double* b2_64;
