@@ -22,8 +22,6 @@ and the uint8 label vector is exchanged so every rank holds all labels.
 `cpu_baseline`: the reference predictor as written, on this box's host cores, on a bounded sample - the only place,
            with --impl reference, where oracle/ code runs.
 """
-from __future__ import annotations
-
 import argparse
 import json
 import os
@@ -662,22 +660,30 @@ def run_e2e_legs(args, cfg, arrs, eng, model, torch, dist, dev, rank, world, lo,
     frame = pd.DataFrame(Xfm.T, columns=[f"pixel_{i}" for i in range(F)], copy=False)
 
     dataset = Dataset(name="bench_dataset", targets=["target"])
+
+    @dataset.reader
+    def reader() -> pd.DataFrame:  # fixes the dataset's datatype (features arrive through Model.predict(features=...))
+        return frame
+
     if kind == "mlp":
         module = torch_module(arrs)
-        app = Model(name="bench_model", init=type(module), dataset=dataset)
+        ModuleT = type(module)
+        app = Model(name="bench_model", init=ModuleT, dataset=dataset)
 
         @app.predictor
-        def predictor(m: type(module), features: pd.DataFrame) -> List[float]:
+        def predictor(m: ModuleT, features: pd.DataFrame) -> List[float]:
             return mlp_argmax(m, features)
 
         model_object = module
     else:
+        from sklearn.linear_model import LogisticRegression
+
         est = sklearn_estimator(arrs, F)
         est.feature_names_in_ = np.asarray(frame.columns, dtype=object)
-        app = Model(name="bench_model", init=type(est), dataset=dataset)
+        app = Model(name="bench_model", init=LogisticRegression, dataset=dataset)
 
         @app.predictor
-        def predictor(estimator: type(est), features: pd.DataFrame) -> List[float]:
+        def predictor(estimator: LogisticRegression, features: pd.DataFrame) -> List[float]:
             return linear_argmax(estimator, features)
 
         model_object = est

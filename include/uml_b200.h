@@ -75,7 +75,7 @@ typedef struct uml_stats {
   int32_t kernel_launches; /* kernels of this library launched by the call                                            */
   int32_t path;            /* 1 = TMA fp32 tile kernel, 2 = generic fp64 kernel, 3 = MLP CUDA-core kernel, 5 = MLP tensor-core
                               (tcgen05) kernel, 4 = small-batch fp64
-                              kernel of the online path (<= 64 rows, one CUDA graph: H2D, kernel, D2H)                 */
+                              kernel of the online path (<= 64 rows: zero-copy request buffer, one kernel replayed as a CUDA graph)                 */
 } uml_stats;
 
 typedef struct uml_device_info {

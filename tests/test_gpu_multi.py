@@ -1,4 +1,5 @@
-"""2-GPU parity of the sharded path (fused peer-store epilogue and NCCL all-gather); skipped on 1-GPU boxes."""
+"""2-GPU parity of the sharded path (fused peer-store epilogue, pipelined push, NCCL all-gather; linear and MLP);
+skipped on 1-GPU boxes - bench.py repeats the float64 check of every rank's rows at N > 1 for that reason."""
 import os
 import subprocess
 import sys
@@ -30,13 +31,35 @@ lo, hi = shard_bounds(N, rank, world); counts = shard_counts(N, world)
 b = eng.stage(X[lo:hi])
 got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True)            # NCCL all-gather
 torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy(), want), "nccl path"
-for dtype, mc, push in ((torch.int32, False, False), (torch.uint8, False, False), (torch.uint8, True, False),
-                        (torch.int32, True, False), (torch.uint8, True, True), (torch.uint8, False, True)):
-    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc, push=push)   # fused stores / two-step push
+variants = ((torch.int32, False, False, 1), (torch.uint8, False, False, 1), (torch.uint8, True, False, 1),
+            (torch.int32, True, False, 1), (torch.uint8, True, True, 1), (torch.uint8, False, True, 1),
+            (torch.uint8, True, True, 4), (torch.uint8, False, True, 3))   # last two: pipelined push (sub-batches)
+for dtype, mc, push, pipe in variants:
+    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc, push=push, pipeline=pipe)   # fused stores / two-step push
     for _ in range(3):
         ex.labels.fill_(99); ex.barrier()
         got = predict_sharded(eng, m, b, row_offset=lo, counts=counts, exact=True, exchange=ex)
-        torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy().astype(np.int32), want), f"fused path {dtype}"
+        torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy().astype(np.int32), want), f"fused path {dtype} {mc} {push} {pipe}"
+# a default Engine (its own non-blocking stream): predict_sharded must order the exchange after the kernels itself
+eng2 = Engine(local); m2 = eng2.load_linear(z["coef"], z["intercept"]); b2 = eng2.stage(X[lo:hi])
+ex = PeerLabelExchange(N, dev, dtype=torch.uint8, multicast=True)
+for _ in range(5):
+    ex.labels.fill_(99); ex.barrier()
+    got = predict_sharded(eng2, m2, b2, row_offset=lo, counts=counts, exact=True, exchange=ex)
+    torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy().astype(np.int32), want), "default-engine stream ordering"
+# the MLP predictor through the same sharded path (cfg 5): tensor-core kernel with fused uint8 stores, and NCCL
+from oracle import mlp as omlp
+g = np.load(os.path.join(os.environ["UML_ROOT"], "tests", "golden", "mlp_64_32_10.npz"))
+mm = eng.load_mlp(g["w1"], g["b1"], g["w2"], g["b2"])
+want_mlp = omlp.predict_indices_f64(X, g["w1"], g["b1"], g["w2"], g["b2"]).astype(np.int32)
+got = predict_sharded(eng, mm, b, row_offset=lo, counts=counts, exact=True)
+torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy(), want_mlp), "mlp nccl path"
+for dtype, mc, push, pipe in ((torch.uint8, True, False, 1), (torch.int32, False, False, 1), (torch.uint8, True, True, 4)):
+    ex = PeerLabelExchange(N, dev, dtype=dtype, multicast=mc, push=push, pipeline=pipe)
+    for _ in range(3):
+        ex.labels.fill_(99); ex.barrier()
+        got = predict_sharded(eng, mm, b, row_offset=lo, counts=counts, exact=True, exchange=ex)
+        torch.cuda.synchronize(); assert np.array_equal(got.cpu().numpy().astype(np.int32), want_mlp), f"mlp fused path {dtype} {mc} {push} {pipe}"
 dist.barrier(); dist.destroy_process_group()
 print(f"rank {rank} ok")
 '''

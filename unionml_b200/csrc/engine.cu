@@ -308,7 +308,7 @@ int uml_engine_create(uml_engine** out, int device_id) {
   if ((err = cudaMalloc(&e->d_flag_count, sizeof(int))) != cudaSuccess) return fail("cudaMalloc", err);
   if ((err = cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", err);
   if ((err = cudaMalloc(&e->d_stage, sizeof(StageResult))) != cudaSuccess) return fail("cudaMalloc", err);
-  if ((err = cudaHostAlloc((void**)&e->h, sizeof(HostMirror), cudaHostAllocDefault)) != cudaSuccess)
+  if ((err = cudaHostAlloc((void**)&e->h, sizeof(HostMirror), cudaHostAllocMapped)) != cudaSuccess)
     return fail("cudaHostAlloc", err);
   memset(e->h, 0, sizeof(HostMirror));
   // the scoring steps do not memset these: the re-score kernel hands the flag list back empty (linear_kernels.cu)
@@ -343,9 +343,7 @@ void uml_engine_destroy(uml_engine* e) {
   delete e->pool;
   for (auto& g : e->small_graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
-  if (e->h_req) cudaFreeHost(e->h_req);
-  cudaFree(e->d_req);
-  cudaFree(e->d_small);
+  if (e->h_req) cudaFreeHost(e->h_req);  // d_req / d_small are device aliases of pinned host memory
   if (e->h) cudaFreeHost(e->h);
   for (auto ev : e->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1059,8 +1057,9 @@ int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst,
 // ---------------------------------------------------------------------------------------------------------------
 // host rows -> host labels
 // ---------------------------------------------------------------------------------------------------------------
-// B <= kSmallRows: request block -> pinned buffer -> (graph: H2D, linear_small_kernel, D2H) -> labels.  fp64 from the
-// caller's own values, so the result is the exact-mode result for either mode.
+// B <= kSmallRows: request block -> pinned (device-mapped) buffer -> linear_small_kernel (replayed as a CUDA graph) ->
+// labels written straight into pinned host memory.  fp64 from the caller's own values, so the result is the
+// exact-mode result for either mode.
 static int predict_host_small(uml_engine* e, const uml_model* m, const void* host_ptr, int n_rows, int F,
                               const SrcLayout& L, int src_dtype, int32_t* labels_out, double* values_out,
                               const double* classes, int n_classes, uml_stats* stats) {
@@ -1068,9 +1067,13 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
   const size_t width = (size_t)F * L.elem;
   const size_t bytes = width * (size_t)n_rows;
   if (!e->h_req) {
-    UML_CUDA(e, cudaHostAlloc(&e->h_req, (size_t)kSmallBytes, cudaHostAllocDefault));
-    UML_CUDA(e, cudaMalloc(&e->d_req, (size_t)kSmallBytes));
-    UML_CUDA(e, cudaMalloc((void**)&e->d_small, sizeof(uml::SmallResult) * kSmallRows));
+    // zero-copy: the kernel reads the request straight from page-locked host memory over PCIe (16 KiB for 32 x 64
+    // float64) and writes the labels straight back - no H2D / D2H copy nodes on the latency path
+    UML_CUDA(e, cudaHostAlloc(&e->h_req, (size_t)kSmallBytes, cudaHostAllocMapped));
+    UML_CUDA(e, cudaHostGetDevicePointer(&e->d_req, e->h_req, 0));
+    void* d_small = nullptr;
+    UML_CUDA(e, cudaHostGetDevicePointer(&d_small, e->h->small, 0));
+    e->d_small = (uml::SmallResult*)d_small;
   }
   // gather into the pinned request buffer as compact row-major rows (the kernel reads any order, but a compact
   // block keeps the H2D copy one contiguous piece)
@@ -1096,12 +1099,7 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
     }
   }
   uml::SrcView view{e->d_req, src_dtype, (long long)F, 1};
-  auto enqueue = [&](cudaStream_t s) -> cudaError_t {
-    cudaError_t ce;
-    if ((ce = cudaMemcpyAsync(e->d_req, e->h_req, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return ce;
-    if ((ce = uml::launch_linear_small(m->dm, view, n_rows, e->d_small, s)) != cudaSuccess) return ce;
-    return cudaMemcpyAsync(e->h->small, e->d_small, sizeof(uml::SmallResult) * (size_t)n_rows, cudaMemcpyDeviceToHost, s);
-  };
+  auto enqueue = [&](cudaStream_t s) -> cudaError_t { return uml::launch_linear_small(m->dm, view, n_rows, e->d_small, s); };
   static const bool no_graph = getenv("UML_B200_NO_GRAPH") != nullptr;
   bool launched = false;
   if (e->small_graph_ok && !no_graph) {
@@ -1156,7 +1154,7 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
     stats->n_ambiguous = n_amb;
     stats->kernel_launches = 1;
     stats->path = 4;
-    stats->h2d_bytes = (int64_t)bytes;
+    stats->h2d_bytes = (int64_t)bytes;  // read by the kernel over PCIe (zero-copy), not by a copy engine
     stats->d2h_bytes = (int64_t)sizeof(uml::SmallResult) * n_rows;
   }
   if (n_bad > 0) UML_FAIL(e, UML_ERR_NONFINITE, "Input X contains NaN or infinity.");
@@ -1486,6 +1484,12 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
   *out = nullptr;
   if (n_in < 1 || n_hidden < 1 || n_out < 2 || n_hidden > 256)
     UML_FAIL(e, UML_ERR_UNSUPPORTED, "MLP shape %d -> %d -> %d (need hidden <= 256, out >= 2)", n_in, n_hidden, n_out);
+  {  // the fp64 re-score kernel keeps W1, W2 and eight row strips in shared memory
+    const size_t need = ((size_t)n_in * n_hidden + (size_t)n_out * (n_hidden + 1) + n_hidden + n_out + 8 * ((size_t)n_in + 2 * n_hidden)) * 8;
+    if (need > (size_t)uml::kMaxSmemBytes)
+      UML_FAIL(e, UML_ERR_UNSUPPORTED, "MLP shape %d -> %d -> %d: fp64 weights (%zu B) exceed the shared memory of one SM", n_in,
+               n_hidden, n_out, need);
+  }
   UML_CUDA(e, cudaSetDevice(e->device));
   const int F = n_in, H = n_hidden, C = n_out;
   const int HP = H + 4, cp = (C + 1 + 3) / 4 * 4;

@@ -18,6 +18,7 @@
 
 #include "uml_common.cuh"
 #include "tma_ring.cuh"
+#include "rescore_util.cuh"
 
 
 namespace uml {
@@ -40,7 +41,9 @@ struct RowScore {
   bool ambiguous;  // fp64 top-2 margin inside the fp64 rounding bound: a true tie, decided by the first-index rule
 };
 
-// float64 scores of one row by one warp (lanes over features, butterfly sums), first maximum wins like np.argmax.
+// float64 scores of one row by one warp, first maximum wins like np.argmax.  Lanes split the features; classes are
+// scored sixteen at a time (each feature value is loaded once per round, 32 independent fp64 chains per lane), the
+// sixteen sums are reduced with warp_reduce16 and the arg-max / runner-up found by a butterfly over the lanes.
 // LOAD(f) yields feature f of the row as double.
 template <typename LOAD>
 __device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, const double* __restrict__ b64,
@@ -49,29 +52,45 @@ __device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __res
   bool bad = false;
   double best = 0.0, second = -INFINITY, amax = 0.0;
   int idx = 0;
-  for (int c = 0; c < C; ++c) {
-    const double* wc = w64 + static_cast<long long>(c) * F;
-    double s = 0.0, a = 0.0;
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    double s[16], a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s[q] = a[q] = 0.0;
     for (int f = lane; f < F; f += 32) {
       const double xv = load(f);
-      if (c == 0 && !isfinite(xv)) bad = true;
-      const double w = wc[f];
-      s = fma(xv, w, s);
-      a = fma(fabs(xv), fabs(w), a);
+      if (!isfinite(xv)) bad = true;
+      const double ax = fabs(xv);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (c0 + q < C) {
+          const double w = w64[static_cast<long long>(c0 + q) * F + f];
+          s[q] = fma(xv, w, s[q]);
+          a[q] = fma(ax, fabs(w), a[q]);
+        }
+      }
     }
-    s = warp_sum(s) + b64[c];
-    a = warp_sum(a) + fabs(b64[c]);
-    amax = fmax(amax, a);
-    if (c == 0) {
-      best = s;
-    } else if (s > best) {
-      second = best;
-      best = s;
-      idx = c;
+    const double sv = warp_reduce16(s, lane), av = warp_reduce16(a, lane);
+    const int cl = c0 + (lane >> 1);  // the class this lane pair now holds
+    const bool valid = cl < C;
+    Top2 t;
+    t.best = valid ? sv + b64[cl] : -INFINITY;
+    t.second = -INFINITY;
+    t.idx = cl;
+    top2_butterfly(t, 2);
+    amax = fmax(amax, warp_max(valid ? av + fabs(b64[cl]) : 0.0, 2));
+    if (c0 == 0) {
+      best = t.best;
+      second = t.second;
+      idx = t.idx;
+    } else if (t.best > best) {  // strict: a tie keeps the earlier (lower) class
+      second = fmax(best, t.second);
+      best = t.best;
+      idx = t.idx;
     } else {
-      second = fmax(second, s);
+      second = fmax(second, t.best);
     }
   }
+  if (idx >= C) idx = 0;  // only reachable with NaN scores, which are reported through `bad`
   RowScore r;
   r.idx = idx;
   r.bad = __any_sync(0xffffffffu, bad);
@@ -652,8 +671,11 @@ static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKer
 }
 
 bool linear_inline_rescore_default() {
-  // UML_B200_INLINE_RESCORE=0 keeps the round-1 scheme (flag list + rescore_f64_kernel) for A/B runs
-  static const bool on = !(getenv("UML_B200_INLINE_RESCORE") && getenv("UML_B200_INLINE_RESCORE")[0] == '0');
+  // Default OFF.  Re-scoring a flagged row inside the tile kernel (by its own warp, right in the epilogue) removes the
+  // second launch but lost the same-box A/B of round 2: 10M rows 0.397 vs 0.375 ms per step, 1.25M rows 70.1 vs
+  // 65.7 us (profiles/r02_ab.json) - the extra ballots and the out-of-line fp64 call cost every tile more than the
+  // launch they save.  UML_B200_INLINE_RESCORE=1 switches it on for re-measurement.
+  static const bool on = getenv("UML_B200_INLINE_RESCORE") && getenv("UML_B200_INLINE_RESCORE")[0] == '1';
   return on;
 }
 
@@ -730,7 +752,11 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
   p.row_offset = l.row_offset;
   p.counters = flags.counters;
-  long long blocks = static_cast<long long>(sm_count) * 8;
+  // flagged rows are few (0.02 % on cfg 2): a grid of 2 blocks per SM starts and drains faster than 8; the all-rows
+  // path (generic shapes) wants every resident warp
+  static int per_sm = 0;
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_f64_kernel, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+  long long blocks = static_cast<long long>(sm_count) * (all_rows ? per_sm : std::min(per_sm, 2));
   if (all_rows) blocks = std::min<long long>(blocks, (l.n_rows + 7) / 8);
   rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream>>>(p);
   return cudaGetLastError();

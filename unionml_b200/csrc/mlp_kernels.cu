@@ -19,6 +19,7 @@
 
 #include "uml_common.cuh"
 #include "tma_ring.cuh"
+#include "rescore_util.cuh"
 
 #ifndef UML_MLP_UNROLL_Q
 #define UML_MLP_UNROLL_Q 8  // feature-quad unroll of the layer-1 loop (same-box A/B, EXACT: 1 -> 1.120, 2 -> 1.056, 4 -> 1.023, 8 -> 1.015 ms)
@@ -284,8 +285,30 @@ struct MlpRescoreParams {
   unsigned long long* counters;
 };
 
+// Shared-memory version: W1 (fp64, [F][H]), W2 ([C][H+1], padded rows) and the biases are staged once per block; per
+// row the warp loads x with one coalesced access, keeps it (as doubles) and the hidden activations in its own
+// shared-memory strip, and every inner-loop operand is a broadcast / conflict-free LDS.  Layer 1: lane per hidden
+// unit, four independent fp64 chains over the features.  Layer 2: lane per class (no warp reductions), then one
+// butterfly for arg-max and runner-up.  ~1 us per row instead of ~10 us for the global-memory loop this replaces.
 __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ double rs_smem[];
+  const int F = p.F, H = p.H, C = p.C;
+  const int HP = H + 1;
+  double* w1s = rs_smem;                 // [F][H]
+  double* w2s = w1s + F * H;             // [C][H + 1]
+  double* b1s = w2s + C * HP;            // [H]
+  double* b2s = b1s + H;                 // [C]
+  double* strips = b2s + C;              // per warp: xs[F] | hv[H] | he[H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* xs = strips + warp * (F + 2 * H);
+  double* hv = xs + F;
+  double* he = hv + H;
+  for (int i = threadIdx.x; i < F * H; i += blockDim.x) w1s[i] = p.w1[i];
+  for (int i = threadIdx.x; i < C * H; i += blockDim.x) w2s[(i / H) * HP + (i % H)] = p.w2[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) b1s[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = p.b2[i];
+  __syncthreads();
+
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
@@ -295,55 +318,80 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
     const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
     const float* xr = p.x + row * p.ld;
     bool bad = false;
-    for (int f = lane; f < p.F; f += 32) bad |= !isfinite(xr[f]);
-    bad = __any_sync(0xffffffffu, bad);
-    // hidden units of this lane: n = lane, lane + 32, ... (H <= 256; the quickstart has 32: one per lane)
-    double hval[8], herr[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int hn = lane + 32 * t;
-      hval[t] = 0.0;
-      herr[t] = 0.0;
-      if (hn < p.H) {
-        const double* w1n = p.w1 + hn;  // w1 is [F][H]: the warp's 32 hidden units read 256 contiguous bytes per feature
-        double hsum = p.b1[hn], habs = fabs(p.b1[hn]);
-#pragma unroll 8
-        for (int f = 0; f < p.F; ++f) {
-          const double xv = static_cast<double>(xr[f]);
-          const double w = w1n[static_cast<long long>(f) * p.H];
-          hsum = fma(xv, w, hsum);
-          habs = fma(fabs(xv), fabs(w), habs);
-        }
-        hval[t] = fmax(hsum, 0.0);
-        herr[t] = (p.F + 2.0) * u * habs;  // the hidden unit's own fp64 rounding error
-      }
+    for (int f = lane; f < F; f += 32) {
+      const float xf = xr[f];
+      bad |= !isfinite(xf);
+      xs[f] = static_cast<double>(xf);
     }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();  // the strip writes above are read by other lanes below
+    // ---- hidden layer: lane per unit, four chains over the features ----
+    for (int hn = lane; hn < H; hn += 32) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int f = 0;
+      for (; f + 4 <= F; f += 4) {
+        const double x0 = xs[f], x1 = xs[f + 1], x2 = xs[f + 2], x3 = xs[f + 3];
+        const double w0 = w1s[f * H + hn], w1 = w1s[(f + 1) * H + hn], w2 = w1s[(f + 2) * H + hn], w3 = w1s[(f + 3) * H + hn];
+        s0 = fma(x0, w0, s0);
+        s1 = fma(x1, w1, s1);
+        s2 = fma(x2, w2, s2);
+        s3 = fma(x3, w3, s3);
+        a0 = fma(fabs(x0), fabs(w0), a0);
+        a1 = fma(fabs(x1), fabs(w1), a1);
+        a2 = fma(fabs(x2), fabs(w2), a2);
+        a3 = fma(fabs(x3), fabs(w3), a3);
+      }
+      for (; f < F; ++f) {
+        const double x0 = xs[f], w0 = w1s[f * H + hn];
+        s0 = fma(x0, w0, s0);
+        a0 = fma(fabs(x0), fabs(w0), a0);
+      }
+      const double hsum = ((s0 + s1) + (s2 + s3)) + b1s[hn];
+      const double habs = ((a0 + a1) + (a2 + a3)) + fabs(b1s[hn]);
+      hv[hn] = fmax(hsum, 0.0);
+      he[hn] = (F + 6.0) * u * habs;  // the hidden unit's own fp64 rounding error (four partial chains + their sum)
+    }
+    __syncwarp();
+    // ---- output layer: lane per class ----
     double best = 0.0, second = -INFINITY, amax = 0.0;
     int idx = 0;
-    for (int c = 0; c < p.C; ++c) {
-      double s = 0.0, a = 0.0;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int hn = lane + 32 * t;
-        if (hn < p.H) {
-          const double w2 = p.w2[static_cast<long long>(c) * p.H + hn];
-          s = fma(hval[t], w2, s);
-          a += fabs(w2) * (hval[t] + herr[t]);
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      double s0 = 0.0, s1 = 0.0, a0 = 0.0, a1 = 0.0;
+      if (c < C) {
+        const double* w2c = w2s + c * HP;
+        int nn = 0;
+        for (; nn + 2 <= H; nn += 2) {
+          const double w0 = w2c[nn], w1 = w2c[nn + 1];
+          s0 = fma(hv[nn], w0, s0);
+          s1 = fma(hv[nn + 1], w1, s1);
+          a0 += fabs(w0) * (hv[nn] + he[nn]);
+          a1 += fabs(w1) * (hv[nn + 1] + he[nn + 1]);
+        }
+        for (; nn < H; ++nn) {
+          s0 = fma(hv[nn], w2c[nn], s0);
+          a0 += fabs(w2c[nn]) * (hv[nn] + he[nn]);
         }
       }
-      s = warp_sum(s) + p.b2[c];
-      a = warp_sum(a) + fabs(p.b2[c]);
-      amax = fmax(amax, a);
-      if (c == 0) {
-        best = s;
-      } else if (s > best) {
-        second = best;
-        best = s;
-        idx = c;
+      Top2 t;
+      t.best = c < C ? (s0 + s1) + b2s[c] : -INFINITY;
+      t.second = -INFINITY;
+      t.idx = c;
+      top2_butterfly(t, 1);
+      amax = fmax(amax, warp_max(c < C ? (a0 + a1) + fabs(b2s[c]) : 0.0, 1));
+      if (c0 == 0) {
+        best = t.best;
+        second = t.second;
+        idx = t.idx;
+      } else if (t.best > best) {
+        second = fmax(best, t.second);
+        best = t.best;
+        idx = t.idx;
       } else {
-        second = fmax(second, s);
+        second = fmax(second, t.best);
       }
     }
+    if (idx >= C) idx = 0;
     if (lane == 0) {
       if (p.labels) p.labels[row] = idx;
       for (int q = 0; q < p.n_peers; ++q) {
@@ -351,9 +399,10 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
         else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
       }
       if (bad) atomicAdd(&p.counters[1], 1ull);
-      const double err = (static_cast<double>(p.F + p.H) + 16.0) * u * amax;
+      const double err = (static_cast<double>(F + H) + 16.0) * u * amax;
       if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
     }
+    __syncwarp();  // the strip is reused by the next row
   }
   // hand the flag list back empty (see rescore_f64_kernel in linear_kernels.cu)
   __syncthreads();
@@ -471,9 +520,21 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   for (int i = 0; i < 8; ++i) p.peers[i] = i < out.n_peers ? out.peers[i] : nullptr;
   p.row_offset = out.row_offset;
   p.counters = flags.counters;
-  long long blocks = static_cast<long long>(sm_count) * 8;
+  // shared memory: W1 + padded W2 + biases + one strip (x, hidden values, hidden errors) per warp
+  const size_t F = m.n_in, H = m.n_hidden, C = m.n_classes;
+  const size_t smem = (F * H + C * (H + 1) + H + C + 8 * (F + 2 * H)) * sizeof(double);
+  if (smem > static_cast<size_t>(kMaxSmemBytes)) return cudaErrorInvalidValue;  // uml_mlp_load bounds F * H
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(mlp_rescore_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_rescore_f64_kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long long blocks = static_cast<long long>(sm_count) * per_sm;  // persistent: every resident warp loops over rows
   if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 7) / 8);
-  mlp_rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream>>>(p);
+  mlp_rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -20,13 +20,14 @@
 // truncating 9-addend aligner with no guard bits), propagates it through layer 2 exactly like the
 // CUDA-core kernel, and re-scores rows whose logit margin is inside the bound in fp64 (mlp_rescore_f64_kernel).
 //
-// Roles (10 warps, one CTA per SM, persistent over 128-row tiles):
-//   warp 8  : TMA producer - 128 x 32 fp32 boxes of X (16 KiB, SWIZZLE_128B) into an S-stage ring
-//   warp 9  : MMA issuer   - one lane; per box 4 x tcgen05.mma (M128, N=2H, K8) from the box (A, K-major SW128) and
+// Roles (14 warps, one CTA per SM, persistent over 128-row tiles):
+//   warp 12 : TMA producer - 128 x 32 fp32 boxes of X (16 KiB, SWIZZLE_128B) into an S-stage ring
+//   warp 13 : MMA issuer   - one lane; per box 4 x tcgen05.mma (M128, N=2H, K8) from the box (A, K-major SW128) and
 //             the resident W1 tile (B); tcgen05.commit frees the ring stage / publishes the accumulator
-//   warps 0-3: scan         - thread per row: A1 bound + tf32-exactness of the row from the same box (LDS.128)
-//   warps 4-7: epilogue     - tcgen05.ld the row's 2H accumulators, + b1, ReLU, layer 2 from constant-bank operands,
-//             argmax (first maximum wins), margin guard, label store (+ peer / multicast stores)
+//   warps 0-3 : scan        - thread per row: A1 bound + tf32-exactness of the row from the same box (LDS.128)
+//   warps 4-11: epilogue    - two sets of four warps taking alternate tiles (the first ncu capture showed one set
+//             80 % busy and everything else waiting on it): tcgen05.ld the row's 2H accumulators, + b1, ReLU, layer 2
+//             from constant-bank operands, argmax (first maximum wins), margin guard, label store (+ peer stores)
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -37,7 +38,9 @@
 
 namespace uml {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 448;
+constexpr int kTcProducerWarp = 12;
+constexpr int kTcMmaWarp = 13;
 constexpr int kTcAccStages = 4;    // TMEM accumulator stages (tiles in flight between MMA and epilogue)
 constexpr int kTcSlots = 32;       // A1 hand-off slots (scan -> epilogue); > the scan warps' maximum lead over the epilogue
 constexpr int kTcMaxFpad = 128;    // features (padded to 32) the resident W1 tile is sized for
@@ -112,7 +115,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     for (int s = 0; s < kTcSlots; ++s) mbar_init(&a1_bar[s], 4);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_base_s);
+  if (warp == kTcMmaWarp) tmem_alloc<TMEM_COLS>(tmem_base_s);
   fence_proxy_async_smem();  // the W1 tile was written with st.shared; UMMA reads it through the async proxy
   tcgen05_fence_before();
   __syncthreads();
@@ -122,7 +125,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   const long long G = gridDim.x;
   const long long num_tiles = p.num_tiles;
 
-  if (warp == 8) {
+  if (warp == kTcProducerWarp) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
       tma_prefetch_desc(&xmap);
@@ -142,7 +145,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kTcMmaWarp) {
     // ===================== MMA issuer (one lane) =====================
     if (elect_one_sync()) {
       int stage = 0;
@@ -212,11 +215,12 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       if (lane == 0) mbar_arrive(&a1_bar[slot]);
     }
   } else {
-    // ===================== epilogue warps 4..7: TMEM lane = row =====================
+    // ===================== epilogue warps 4..11: TMEM lane = row; set 0 (warps 4-7) even tiles, set 1 odd tiles ====
     const int wq = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
+    const int set = (warp - 4) >> 2;
     const int row_in_tile = wq * 32 + lane;
-    uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += G, ++it) {
+    uint32_t it = static_cast<uint32_t>(set);
+    for (long long tile = blockIdx.x + set * G; tile < num_tiles; tile += 2 * G, it += 2) {
       const uint32_t acc = it % kTcAccStages;
       const uint32_t acc_phase = (it / kTcAccStages) & 1u;
       const uint32_t slot = it % kTcSlots;
@@ -310,7 +314,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kTcMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }

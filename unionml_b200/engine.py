@@ -86,6 +86,10 @@ class LinearModel:
         self.n_features = n_features
         self.n_classes = n_classes
         self.classes = classes
+        # numeric class labels as float64, ready for the device-side classes_.take (None for string labels)
+        self.classes_f64 = None
+        if classes is not None and np.asarray(classes).dtype.kind in "iufb":
+            self.classes_f64 = np.ascontiguousarray(classes, dtype=np.float64)
         self._fin = weakref.finalize(self, N.lib().uml_model_free, handle)
 
     def set_affine(self, shift=None, scale=None) -> None:
@@ -421,7 +425,8 @@ class Engine:
         """Host rows -> ``classes_[argmax]`` as a float64 host vector: the pipelined call with ``classes_.take`` and the
         float conversion of the canonical predictor (``README.md:92``) done on the device, chunk by chunk."""
         arr = as_feature_array(features)
-        classes = np.ascontiguousarray(classes, dtype=np.float64)
+        if not (isinstance(classes, np.ndarray) and classes.dtype == np.float64 and classes.flags.c_contiguous):
+            classes = np.ascontiguousarray(classes, dtype=np.float64)
         out = np.empty(arr.shape[0], dtype=np.float64)
         stats = N.Stats()
         with self._lock:

@@ -236,13 +236,12 @@ def linear_argmax(estimator: Any, features: Any) -> List[float]:
 
     Numeric ``classes_`` (the canonical case): ``classes_.take`` and the float conversion run on the device
     (``uml_linear_predict_host_values``) and the float64 vector becomes the list in one ``tolist()``."""
-    classes = getattr(estimator, "classes_", None)
-    if classes is not None and np.asarray(classes).dtype.kind in "iufb":
-        engine = get_engine()
-        dm = device_model(estimator, engine)
+    engine = get_engine()
+    dm = device_model(estimator, engine)
+    if dm.classes_f64 is not None:
         _check_feature_names(estimator, features)
         _check_min_samples(features)
-        values, stats = engine.predict_host_values(dm, features, np.asarray(classes, dtype=np.float64), exact=_exact_default())
+        values, stats = engine.predict_host_values(dm, features, dm.classes_f64, exact=_exact_default())
         _note_ambiguous(stats)
         return values.tolist()
     return [float(x) for x in linear_predict_labels(estimator, features)]
