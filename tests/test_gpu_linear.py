@@ -60,7 +60,7 @@ def test_committed_fixture(engine, digits_model, synthetic_digits):
         b = engine.stage(arr)
         idx2, st2 = engine.predict(m, b, exact=True)
         np.testing.assert_array_equal(idx2, idx)
-        assert st2["path"] == 1 and st2["kernel_launches"] == 1  # flagged rows are re-scored inside the tile kernel
+        assert st2["path"] == 1 and st2["kernel_launches"] == 2  # tile kernel + fp64 re-score of the flagged rows
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -138,7 +138,8 @@ def test_layouts_and_dtypes(engine, digits_model):
 
 
 def test_inline_and_list_rescore_agree(engine, digits_model):
-    """UML_B200_INLINE_RESCORE=0 keeps the round-1 scheme (flag list + rescore_f64_kernel); same labels, same counters."""
+    """UML_B200_INLINE_RESCORE=1 re-scores flagged rows inside the tile kernel (kept as an A/B switch: it lost the same-box
+    comparison, profiles/r02_ab.json); the default is the flag list + rescore_f64_kernel.  Same labels, same counters."""
     import os
     import subprocess
     import sys
