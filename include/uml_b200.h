@@ -169,6 +169,17 @@ UML_API int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, co
                                    int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
                                    const double* classes_host, int n_classes, double* values_out, int mode,
                                    int64_t chunk_rows, uml_stats* stats);
+/* asynchronous form of uml_linear_predict_host_values: _begin returns at once and the pipeline runs on a library thread;
+ * uml_async_poll reports how long a prefix of values_out is final (the caller may read it - the Python predictor turns
+ * it into list pieces while the rest of the batch is still in flight); uml_async_finish joins and returns the call's
+ * status (UML_ERR_NONFINITE ...) and stats.  One asynchronous call per engine; no other call on the engine until
+ * _finish.  host_ptr / values_out must stay valid until then. */
+UML_API int uml_linear_predict_host_values_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
+                                         int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes,
+                                         int src_dtype, const double* classes_host, int n_classes, double* values_out,
+                                         int mode, int64_t chunk_rows);
+UML_API int uml_async_poll(uml_engine* e, int64_t* rows_done, int* finished);
+UML_API int uml_async_finish(uml_engine* e, uml_stats* stats);
 /* class probabilities of a resident batch: LogisticRegression.predict_proba (sklearn/linear_model/_logistic.py) =
  * softmax of decision_function (sigmoid for the binary layout: columns [1 - p, p]).  fp32 scores and exp;
  * proba_out: n_rows x n_classes row-major fp32 (n_classes = 2 for a binary model), host or device memory. */

@@ -165,6 +165,32 @@ def test_online_shape_small_batches(engine, digits_model):
     np.testing.assert_array_equal(after, want)
 
 
+def test_large_frames_build_the_list_while_the_batch_is_in_flight(engine, digits_model):
+    """>= 1M rows: ``linear_argmax`` runs the pipeline on a library thread (``uml_linear_predict_host_values_begin``)
+    and turns the finished prefix into list pieces meanwhile.  Same labels; NaN still raises; the engine is usable after."""
+    from unionml_b200.predictors import linear_argmax
+
+    coef, intercept = digits_model["coef"], digits_model["intercept"]
+    est = _estimator(coef, intercept, digits_model["classes"])
+    N = 1_300_003
+    X = np.random.default_rng(17).integers(0, 17, size=(64, N)).astype(np.float64)  # feature-major block
+    frame = pd.DataFrame(X.T, columns=[f"pixel_{i}" for i in range(64)], copy=False)
+    est.feature_names_in_ = np.asarray(frame.columns, dtype=object)
+    want = est.predict(frame).astype(np.float64)
+    for _ in range(2):
+        got = linear_argmax(est, frame)
+        assert isinstance(got, list) and len(got) == N and isinstance(got[0], float)
+        np.testing.assert_array_equal(np.asarray(got), want)
+    out, st = engine.predict_host_values_list(engine.load_linear(coef, intercept), X.T, np.arange(10.0), chunk_rows=8192)
+    np.testing.assert_array_equal(np.asarray(out), want)
+    assert st["n_rows"] == N
+    bad = X.T.copy()
+    bad[N // 2, 5] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        linear_argmax(est, pd.DataFrame(bad, columns=frame.columns))
+    assert linear_argmax(est, frame.iloc[:1000]) == want[:1000].tolist()
+
+
 def test_values_route_equals_take(engine, digits_model):
     coef, intercept = digits_model["coef"], digits_model["intercept"]
     classes = np.array([3.0, 1.5, -2.0, 7.0, 9.0, 11.0, 0.0, 4.0, 5.0, 6.0])

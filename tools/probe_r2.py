@@ -179,6 +179,31 @@ def main():
         stg[name] = {"stage_s": min(ts), "GBps_in": rows * 64 * 8 / min(ts) / 1e9}
     out["stage_calls"] = stg
 
+    # ---- (6) where the time of the MLP drop-in predictor goes (float64 frame -> List[float])
+    import torch.nn as nn
+
+    from unionml_b200.engine import get_engine
+    from unionml_b200.predictors import device_mlp, mlp_argmax
+
+    zz = np.load(ROOT / "tests" / "golden" / "mlp_64_32_10.npz")
+    module = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
+    with torch.no_grad():
+        module[0].weight.copy_(torch.from_numpy(zz["w1"])); module[0].bias.copy_(torch.from_numpy(zz["b1"]))
+        module[2].weight.copy_(torch.from_numpy(zz["w2"])); module[2].bias.copy_(torch.from_numpy(zz["b2"]))
+    mlp_argmax(module, frame.iloc[:100_000])
+    ge = get_engine()
+    dm = device_mlp(module, ge)
+    tt = {}
+    for rep in range(2):
+        t0 = time.perf_counter(); a = frame.to_numpy(); t1 = time.perf_counter()
+        b = ge.stage(a, keep_f64=False); t2 = time.perf_counter()
+        idx, _ = ge.predict_mlp(dm, b, exact=True); t3 = time.perf_counter()
+        b.free(); t4 = time.perf_counter()
+        lst = idx.astype(np.float64).tolist(); t5 = time.perf_counter()
+        tt = {"to_numpy": t1 - t0, "stage": t2 - t1, "predict_mlp": t3 - t2, "free": t4 - t3, "astype_tolist": t5 - t4}
+    t0 = time.perf_counter(); mlp_argmax(module, frame); tt["mlp_argmax_total"] = time.perf_counter() - t0
+    out["mlp_argmax_4M_breakdown_s"] = tt
+
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "probe_r2.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out, indent=1))

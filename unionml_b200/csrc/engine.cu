@@ -179,6 +179,13 @@ struct uml_engine {
   uml::SmallResult* d_small = nullptr;
   std::vector<SmallGraph> small_graphs;
   uint64_t small_tick = 0;
+  // asynchronous host call (uml_linear_predict_host_values_begin / _poll / _finish): one in flight per engine
+  std::thread async_thread;
+  std::atomic<int64_t> async_rows_done{0};
+  std::atomic<int> async_finished{1};
+  int async_status = UML_OK;
+  uml_stats async_stats{};
+  std::vector<double> async_classes;
   bool small_graph_ok = true;
   HostMirror* h = nullptr;
 };
@@ -325,6 +332,7 @@ int uml_engine_create(uml_engine** out, int device_id) {
 
 void uml_engine_destroy(uml_engine* e) {
   if (!e) return;
+  if (e->async_thread.joinable()) e->async_thread.join();
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   cudaFree(e->d_flag_count);
@@ -1164,7 +1172,7 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
 static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
                              int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
                              double* values_out, const double* classes, int n_classes, int mode, int64_t chunk_rows,
-                             uml_stats* stats) {
+                             uml_stats* stats, std::atomic<int64_t>* progress = nullptr) {
   if (!e || !m || (!host_ptr && n_rows > 0) || (!labels_out && !values_out && n_rows > 0) || n_rows < 0 || n_features < 1)
     return UML_ERR_INVALID;
   if (values_out && (!classes || n_classes < 1)) return UML_ERR_INVALID;
@@ -1180,8 +1188,11 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
   if (rc != UML_OK) return rc;
   const int F = n_features;
-  if (n_rows <= kSmallRows && (int64_t)F * L.elem * n_rows <= kSmallBytes)
-    return predict_host_small(e, m, host_ptr, (int)n_rows, F, L, src_dtype, labels_out, values_out, classes, n_classes, stats);
+  if (n_rows <= kSmallRows && (int64_t)F * L.elem * n_rows <= kSmallBytes) {
+    rc = predict_host_small(e, m, host_ptr, (int)n_rows, F, L, src_dtype, labels_out, values_out, classes, n_classes, stats);
+    if (progress && rc == UML_OK) progress->store(n_rows);
+    return rc;
+  }
 
   NvtxRange r_all("uml:predict_host");
   const int64_t ld = (F + 3) / 4 * 4;
@@ -1229,7 +1240,9 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   // A device-to-host copy into PAGEABLE memory blocks the calling thread until the chunk's whole pipeline has drained,
   // which would serialise gather / H2D / scoring.  Pageable outputs therefore land in pinned slots first and are
   // copied out by the host when the slot comes round again (three chunks later) or at the end.
-  const bool result_bounce = (labels_out && !host_ptr_is_pinned(labels_out)) || (values_out && !host_ptr_is_pinned(values_out));
+  // (the asynchronous variant always does: the flush is also where a finished prefix is published to the poller)
+  const bool result_bounce = progress != nullptr || (labels_out && !host_ptr_is_pinned(labels_out)) ||
+                             (values_out && !host_ptr_is_pinned(values_out));
   if (result_bounce && e->result_cap < chunk_rows * 12) {
     for (auto& p : e->h_result) {
       if (p) cudaFreeHost(p);
@@ -1251,6 +1264,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     if (values_out) memcpy(values_out + pending[sl].r0, base, (size_t)pending[sl].rows * 8);
     if (labels_out) memcpy(labels_out + pending[sl].r0, base + (size_t)chunk_rows * 8, (size_t)pending[sl].rows * 4);
     pending[sl].live = false;
+    if (progress) progress->store(pending[sl].r0 + pending[sl].rows, std::memory_order_release);  // slots flush in row order
     return cudaSuccess;
   };
 
@@ -1450,6 +1464,46 @@ int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, const void
                            values_out, classes_host, n_classes, mode, chunk_rows, stats);
 }
 
+// asynchronous variant: the whole pipeline runs on a library thread so that the caller (Python building the
+// List[float] of the predictor contract, ~15 ns per element) can consume values_out[0, rows_done) while the rest of the
+// batch is still crossing PCIe.  One call in flight per engine; no other call on the engine until _finish.
+int uml_linear_predict_host_values_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
+                                         int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                         const double* classes_host, int n_classes, double* values_out, int mode,
+                                         int64_t chunk_rows) {
+  if (!e || !m || (!values_out && n_rows > 0) || !classes_host || n_classes < 1) return UML_ERR_INVALID;
+  if (!e->async_finished.load() || e->async_thread.joinable())
+    UML_FAIL(e, UML_ERR_INVALID, "an asynchronous call is already in flight on this engine (call uml_async_finish first)");
+  if (n_classes < m->dm.n_classes) UML_FAIL(e, UML_ERR_INVALID, "classes_ has %d entries, the model scores %d classes", n_classes, m->dm.n_classes);
+  e->async_classes.assign(classes_host, classes_host + n_classes);
+  e->async_rows_done.store(0);
+  e->async_finished.store(0);
+  e->async_status = UML_OK;
+  memset(&e->async_stats, 0, sizeof(e->async_stats));
+  e->async_thread = std::thread([=]() {
+    e->async_status = predict_host_impl(e, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype,
+                                        nullptr, values_out, e->async_classes.data(), n_classes, mode, chunk_rows,
+                                        &e->async_stats, &e->async_rows_done);
+    e->async_finished.store(1, std::memory_order_release);
+  });
+  return UML_OK;
+}
+
+int uml_async_poll(uml_engine* e, int64_t* rows_done, int* finished) {
+  if (!e) return UML_ERR_INVALID;
+  const int fin = e->async_finished.load(std::memory_order_acquire);  // read first: rows_done is final once it is set
+  if (rows_done) *rows_done = e->async_rows_done.load(std::memory_order_acquire);
+  if (finished) *finished = fin;
+  return UML_OK;
+}
+
+int uml_async_finish(uml_engine* e, uml_stats* stats) {
+  if (!e) return UML_ERR_INVALID;
+  if (e->async_thread.joinable()) e->async_thread.join();
+  if (stats) *stats = e->async_stats;
+  return e->async_status;
+}
+
 int uml_linear_predict_proba(uml_engine* e, const uml_model* m, const uml_batch* b, float* proba_out, int proba_on_device) {
   if (!e || !m || !b || (!proba_out && b->n_rows > 0)) return UML_ERR_INVALID;
   if (b->n_features != m->n_features_in)
@@ -1485,7 +1539,8 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
   if (n_in < 1 || n_hidden < 1 || n_out < 2 || n_hidden > 256)
     UML_FAIL(e, UML_ERR_UNSUPPORTED, "MLP shape %d -> %d -> %d (need hidden <= 256, out >= 2)", n_in, n_hidden, n_out);
   {  // the fp64 re-score kernel keeps W1, W2 and eight row strips in shared memory
-    const size_t need = ((size_t)n_in * n_hidden + (size_t)n_out * (n_hidden + 1) + n_hidden + n_out + 8 * ((size_t)n_in + 2 * n_hidden)) * 8;
+    const size_t need = ((size_t)n_in * n_hidden + (size_t)n_out * (n_hidden + 1) + 2 * (size_t)n_hidden + n_out + n_in +
+                         8 * ((size_t)n_in + n_hidden)) * 8;
     if (need > (size_t)uml::kMaxSmemBytes)
       UML_FAIL(e, UML_ERR_UNSUPPORTED, "MLP shape %d -> %d -> %d: fp64 weights (%zu B) exceed the shared memory of one SM", n_in,
                n_hidden, n_out, need);

@@ -190,6 +190,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
   }
   __syncthreads();
 
+  pdl_launch_dependents();  // the re-score kernel behind this launch may be scheduled now; it waits for this grid to finish
   const long long G = gridDim.x;
   const long long num_tiles = p.num_tiles;
   const int KC = p.kc;
@@ -431,6 +432,7 @@ struct RescoreParams {
 
 
 __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
+  pdl_wait_for_predecessor();  // the flag list is written by the scoring kernel this launch depends on
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -758,8 +760,7 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_f64_kernel, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
   long long blocks = static_cast<long long>(sm_count) * (all_rows ? per_sm : std::min(per_sm, 2));
   if (all_rows) blocks = std::min<long long>(blocks, (l.n_rows + 7) / 8);
-  rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_dependent(rescore_f64_kernel, static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream, p);
 }
 
 }  // namespace uml

@@ -292,23 +292,42 @@ struct MlpRescoreParams {
 // butterfly for arg-max and runner-up.  ~1 us per row instead of ~10 us for the global-memory loop this replaces.
 __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
   extern __shared__ double rs_smem[];
+  // (weights are staged first: they do not depend on the scoring kernel; the flag list does - see the wait below)
   const int F = p.F, H = p.H, C = p.C;
   const int HP = H + 1;
   double* w1s = rs_smem;                 // [F][H]
   double* w2s = w1s + F * H;             // [C][H + 1]
   double* b1s = w2s + C * HP;            // [H]
   double* b2s = b1s + H;                 // [C]
-  double* strips = b2s + C;              // per warp: xs[F] | hv[H] | he[H]
+  double* w1m = b2s + C;                 // [F]  max_n |w1_nf|
+  double* w2m = w1m + F;                 // [H]  max_c |w2_cn|
+  double* strips = w2m + H;              // per warp: xs[F] | hv[H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* xs = strips + warp * (F + 2 * H);
+  double* xs = strips + warp * (F + H);
   double* hv = xs + F;
-  double* he = hv + H;
   for (int i = threadIdx.x; i < F * H; i += blockDim.x) w1s[i] = p.w1[i];
   for (int i = threadIdx.x; i < C * H; i += blockDim.x) w2s[(i / H) * HP + (i % H)] = p.w2[i];
   for (int i = threadIdx.x; i < H; i += blockDim.x) b1s[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = p.b2[i];
   __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    double m = 0.0;
+    for (int hn = 0; hn < H; ++hn) m = fmax(m, fabs(w1s[f * H + hn]));
+    w1m[f] = m;
+  }
+  for (int hn = threadIdx.x; hn < H; hn += blockDim.x) {
+    double m = 0.0;
+    for (int c = 0; c < C; ++c) m = fmax(m, fabs(w2s[c * HP + hn]));
+    w2m[hn] = m;
+  }
+  double b1max = 0.0, b2max = 0.0;
+  for (int hn = 0; hn < H; ++hn) b1max = fmax(b1max, fabs(b1s[hn]));
+  for (int c = 0; c < C; ++c) b2max = fmax(b2max, fabs(b2s[c]));
+  __syncthreads();
+  double w2sum = 0.0;  // sum_n max_c |w2_cn|: how far a hidden-layer error can move any logit
+  for (int hn = 0; hn < H; ++hn) w2sum += w2m[hn];
 
+  pdl_wait_for_predecessor();  // from here on: the flag list and labels of the scoring kernel this launch depends on
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
@@ -318,67 +337,56 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
     const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
     const float* xr = p.x + row * p.ld;
     bool bad = false;
+    double a1 = 0.0;  // sum_f |x_f| max_n |w1_nf|: bounds every hidden unit's absolute sum (one chain instead of H)
     for (int f = lane; f < F; f += 32) {
       const float xf = xr[f];
       bad |= !isfinite(xf);
-      xs[f] = static_cast<double>(xf);
+      const double xd = static_cast<double>(xf);
+      xs[f] = xd;
+      a1 = fma(fabs(xd), w1m[f], a1);
     }
     bad = __any_sync(0xffffffffu, bad);
+    a1 = warp_sum(a1) + b1max;
+    const double herr = (F + 6.0) * u * a1;  // any hidden unit's own fp64 rounding error (four partial chains + their sum)
     __syncwarp();  // the strip writes above are read by other lanes below
     // ---- hidden layer: lane per unit, four chains over the features ----
+    double a2 = 0.0;  // sum_n (h_n + herr) max_c |w2_cn|: bounds every logit's absolute sum
     for (int hn = lane; hn < H; hn += 32) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int f = 0;
       for (; f + 4 <= F; f += 4) {
-        const double x0 = xs[f], x1 = xs[f + 1], x2 = xs[f + 2], x3 = xs[f + 3];
-        const double w0 = w1s[f * H + hn], w1 = w1s[(f + 1) * H + hn], w2 = w1s[(f + 2) * H + hn], w3 = w1s[(f + 3) * H + hn];
-        s0 = fma(x0, w0, s0);
-        s1 = fma(x1, w1, s1);
-        s2 = fma(x2, w2, s2);
-        s3 = fma(x3, w3, s3);
-        a0 = fma(fabs(x0), fabs(w0), a0);
-        a1 = fma(fabs(x1), fabs(w1), a1);
-        a2 = fma(fabs(x2), fabs(w2), a2);
-        a3 = fma(fabs(x3), fabs(w3), a3);
+        s0 = fma(xs[f], w1s[f * H + hn], s0);
+        s1 = fma(xs[f + 1], w1s[(f + 1) * H + hn], s1);
+        s2 = fma(xs[f + 2], w1s[(f + 2) * H + hn], s2);
+        s3 = fma(xs[f + 3], w1s[(f + 3) * H + hn], s3);
       }
-      for (; f < F; ++f) {
-        const double x0 = xs[f], w0 = w1s[f * H + hn];
-        s0 = fma(x0, w0, s0);
-        a0 = fma(fabs(x0), fabs(w0), a0);
-      }
-      const double hsum = ((s0 + s1) + (s2 + s3)) + b1s[hn];
-      const double habs = ((a0 + a1) + (a2 + a3)) + fabs(b1s[hn]);
-      hv[hn] = fmax(hsum, 0.0);
-      he[hn] = (F + 6.0) * u * habs;  // the hidden unit's own fp64 rounding error (four partial chains + their sum)
+      for (; f < F; ++f) s0 = fma(xs[f], w1s[f * H + hn], s0);
+      const double h = fmax(((s0 + s1) + (s2 + s3)) + b1s[hn], 0.0);
+      hv[hn] = h;
+      a2 = fma(h, w2m[hn], a2);
     }
+    const double amax = warp_sum(a2) + herr * w2sum + b2max;
     __syncwarp();
     // ---- output layer: lane per class ----
-    double best = 0.0, second = -INFINITY, amax = 0.0;
+    double best = 0.0, second = -INFINITY;
     int idx = 0;
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int c = c0 + lane;
-      double s0 = 0.0, s1 = 0.0, a0 = 0.0, a1 = 0.0;
+      double s0 = 0.0, s1 = 0.0;
       if (c < C) {
         const double* w2c = w2s + c * HP;
         int nn = 0;
         for (; nn + 2 <= H; nn += 2) {
-          const double w0 = w2c[nn], w1 = w2c[nn + 1];
-          s0 = fma(hv[nn], w0, s0);
-          s1 = fma(hv[nn + 1], w1, s1);
-          a0 += fabs(w0) * (hv[nn] + he[nn]);
-          a1 += fabs(w1) * (hv[nn + 1] + he[nn + 1]);
-        }
-        for (; nn < H; ++nn) {
           s0 = fma(hv[nn], w2c[nn], s0);
-          a0 += fabs(w2c[nn]) * (hv[nn] + he[nn]);
+          s1 = fma(hv[nn + 1], w2c[nn + 1], s1);
         }
+        for (; nn < H; ++nn) s0 = fma(hv[nn], w2c[nn], s0);
       }
       Top2 t;
       t.best = c < C ? (s0 + s1) + b2s[c] : -INFINITY;
       t.second = -INFINITY;
       t.idx = c;
       top2_butterfly(t, 1);
-      amax = fmax(amax, warp_max(c < C ? (a0 + a1) + fabs(b2s[c]) : 0.0, 1));
       if (c0 == 0) {
         best = t.best;
         second = t.second;
@@ -399,7 +407,8 @@ __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescorePa
         else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
       }
       if (bad) atomicAdd(&p.counters[1], 1ull);
-      const double err = (static_cast<double>(F + H) + 16.0) * u * amax;
+      // fp64 error of a logit: the hidden units' own errors carried through W2, plus the output layer's chain
+      const double err = herr * w2sum + (static_cast<double>(H) + 16.0) * u * amax;
       if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
     }
     __syncwarp();  // the strip is reused by the next row
@@ -520,9 +529,9 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   for (int i = 0; i < 8; ++i) p.peers[i] = i < out.n_peers ? out.peers[i] : nullptr;
   p.row_offset = out.row_offset;
   p.counters = flags.counters;
-  // shared memory: W1 + padded W2 + biases + one strip (x, hidden values, hidden errors) per warp
+  // shared memory: W1 + padded W2 + biases + the two bound vectors + one strip (x, hidden values) per warp
   const size_t F = m.n_in, H = m.n_hidden, C = m.n_classes;
-  const size_t smem = (F * H + C * (H + 1) + H + C + 8 * (F + 2 * H)) * sizeof(double);
+  const size_t smem = (F * H + C * (H + 1) + H + C + F + H + 8 * (F + H)) * sizeof(double);
   if (smem > static_cast<size_t>(kMaxSmemBytes)) return cudaErrorInvalidValue;  // uml_mlp_load bounds F * H
   static size_t configured = 0;
   if (smem > configured) {
@@ -534,7 +543,8 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_rescore_f64_kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long blocks = static_cast<long long>(sm_count) * per_sm;  // persistent: every resident warp loops over rows
   if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 7) / 8);
-  mlp_rescore_f64_kernel<<<static_cast<int>(std::max<long long>(1, blocks)), 256, smem, stream>>>(p);
+  cudaError_t lerr = launch_dependent(mlp_rescore_f64_kernel, static_cast<int>(std::max<long long>(1, blocks)), 256, smem, stream, p);
+  if (lerr != cudaSuccess) return lerr;
   return cudaGetLastError();
 }
 

@@ -122,6 +122,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
 
+  pdl_launch_dependents();  // the fp64 re-score behind this launch may stage its weights while this grid runs
   const long long G = gridDim.x;
   const long long num_tiles = p.num_tiles;
 
@@ -134,7 +135,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += G) {
         for (int k = 0; k < KC; ++k) {
-          mbar_wait_bounded(&empty_bar[stage], phase ^ 1u);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_2d(ring + static_cast<size_t>(stage) * kStageBytes, &xmap, &full_bar[stage], k * kChunkF,
                       static_cast<int>(tile * kTileRows), policy);
@@ -156,8 +157,8 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         const uint32_t acc_phase = (it / kTcAccStages) & 1u;
         const uint32_t d_tmem = tmem_base + acc * N;
         for (int k = 0; k < KC; ++k) {
-          mbar_wait_bounded(&full_bar[stage], phase);
-          if (k == 0) mbar_wait_bounded(&dempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+          mbar_wait_relaxed(&full_bar[stage], phase);
+          if (k == 0) mbar_wait_relaxed(&dempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
           tcgen05_fence_after();
           const uint32_t a_base = smem_u32(ring + static_cast<size_t>(stage) * kStageBytes);
           const uint32_t b_base = smem_u32(btile + static_cast<size_t>(k) * N * 128);
@@ -187,7 +188,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       float a1 = 0.f;
       uint32_t lowbits = 0u;
       for (int k = 0; k < KC; ++k) {
-        mbar_wait_bounded(&full_bar[stage], phase);
+        mbar_wait_relaxed(&full_bar[stage], phase);
         const uint8_t* xs = ring + static_cast<size_t>(stage) * kStageBytes;
 #pragma unroll
         for (int q = 0; q < kChunkF / 4; ++q) {

@@ -98,5 +98,14 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (++spins > (1u << 26)) __trap();
   }
 }
+// the same for roles that are ahead of the critical path (producer, scan, MMA issuer): back off between polls so the
+// spinning does not take issue slots from the epilogue warps sharing the sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 
 }  // namespace uml

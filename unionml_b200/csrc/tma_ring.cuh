@@ -77,6 +77,12 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
+// programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor on the stream is still running; it must wait here before touching the
+// predecessor's results.  The predecessor allows that early scheduling with pdl_launch_dependents().
+__device__ __forceinline__ void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -69,6 +70,25 @@ struct LinearLaunch {
   int wire_u8;  // 1: peer vectors are uint8 (one byte per label), 0: int32
   int64_t row_offset;
 };
+
+// launch `kern<<<grid, block, smem, stream>>>(p)` as a programmatic dependent of the previous kernel on the stream: its
+// blocks may become resident while that kernel drains (the kernel itself waits with griddepcontrol.wait), which hides
+// the launch latency between a scoring kernel and its fp64 re-score.  UML_B200_NO_PDL=1 falls back to a plain launch.
+template <typename Params>
+inline cudaError_t launch_dependent(void (*kern)(Params), int grid, int block, size_t smem, cudaStream_t stream, const Params& p) {
+  static const bool no_pdl = getenv("UML_B200_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
 
 // scoring kernels (linear_kernels.cu)
 // *rescore_kernel_needed: exact mode with the inline re-score switched off -> the caller launches launch_rescore_f64

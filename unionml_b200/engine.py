@@ -449,6 +449,48 @@ class Engine:
             self._check(st)
         return out, stats.as_dict()
 
+    def predict_host_values_list(self, model: LinearModel, features: Any, classes, exact: bool = True,
+                                 chunk_rows: int = 0) -> Tuple[list, dict]:
+        """``classes_[argmax]`` per row as a Python ``list`` of floats (the predictor contract, ``README.md:87-92``).
+
+        The pipeline runs on a library thread (``uml_linear_predict_host_values_begin``); this thread turns the
+        finished prefix into list pieces while the rest of the batch is still in flight, so list building (~15 ns per
+        element) overlaps PCIe and the GPU."""
+        import time
+
+        arr = as_feature_array(features)
+        if not (isinstance(classes, np.ndarray) and classes.dtype == np.float64 and classes.flags.c_contiguous):
+            classes = np.ascontiguousarray(classes, dtype=np.float64)
+        n = arr.shape[0]
+        values = np.empty(n, dtype=np.float64)
+        stats = N.Stats()
+        out: list = []
+        lib = N.lib()
+        with self._lock:
+            st = lib.uml_linear_predict_host_values_begin(
+                self._h, model._h, C.c_void_p(arr.ctypes.data), n, arr.shape[1], arr.strides[0], arr.strides[1],
+                _DTYPES[arr.dtype], classes.ctypes.data_as(C.c_void_p), len(classes), values.ctypes.data_as(C.c_void_p),
+                N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST, chunk_rows,
+            )
+            self._check(st)
+            done, rows_done, finished = 0, C.c_int64(), C.c_int()
+            try:
+                while True:
+                    lib.uml_async_poll(self._h, C.byref(rows_done), C.byref(finished))
+                    if rows_done.value - done >= 262_144 or (finished.value and rows_done.value > done):
+                        out.extend(values[done : rows_done.value].tolist())
+                        done = rows_done.value
+                    elif finished.value:
+                        break
+                    else:
+                        time.sleep(0.0002)
+            finally:
+                st = lib.uml_async_finish(self._h, C.byref(stats))
+            self._check(st)
+        if done < n:  # not reached when the call succeeded (every chunk is flushed before it finishes)
+            out.extend(values[done:].tolist())
+        return out, stats.as_dict()
+
     def predict_proba(self, model: LinearModel, batch: Batch, out_device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
         """``softmax(X @ coef_.T + intercept_)`` per row (fp32), ``(n_rows, n_classes)``; ``[1 - p, p]`` for a binary model."""
         with self._lock:

@@ -242,61 +242,18 @@ def linear_argmax(estimator: Any, features: Any) -> List[float]:
         _check_feature_names(estimator, features)
         _check_min_samples(features)
         n_rows = getattr(features, "shape", (0,))[0]
-        if n_rows >= _SEGMENT_MIN_ROWS:
-            return _segmented_values_list(engine, dm, features, n_rows)
+        if n_rows >= _ASYNC_LIST_MIN_ROWS:
+            out, stats = engine.predict_host_values_list(dm, features, dm.classes_f64, exact=_exact_default())
+            _note_ambiguous(stats)
+            return out
         values, stats = engine.predict_host_values(dm, features, dm.classes_f64, exact=_exact_default())
         _note_ambiguous(stats)
         return values.tolist()
     return [float(x) for x in linear_predict_labels(estimator, features)]
 
 
-#: batches at least this large are scored in row segments so that building the Python list (the reference contract is
-#: ``List[float]``: ~15 ns per element, 0.15 s per 10M rows) overlaps the H2D / GPU pipeline of the next segment
-_SEGMENT_MIN_ROWS = 2_000_000
-_SEGMENTS = 8
-
-
-def _segmented_values_list(engine: Engine, dm: LinearModel, features: Any, n_rows: int) -> List[float]:
-    """``predict_host_values`` per row segment on the calling thread (the C call releases the GIL) while a helper
-    thread turns the finished segments into list pieces; the pieces are spliced into one list at the end."""
-    import queue
-
-    from unionml_b200.engine import as_feature_array
-
-    arr = as_feature_array(features)
-    step = -(-n_rows // _SEGMENTS)
-    step = (step + 127) // 128 * 128
-    bounds = [(a, min(n_rows, a + step)) for a in range(0, n_rows, step)]
-    out: List[Any] = [None] * n_rows
-    work: "queue.Queue" = queue.Queue()
-    failure: List[BaseException] = []
-
-    def listify():
-        while True:
-            item = work.get()
-            if item is None:
-                return
-            a, b, values = item
-            try:
-                out[a:b] = values.tolist()
-            except BaseException as exc:  # surfaced on the calling thread
-                failure.append(exc)
-
-    helper = threading.Thread(target=listify, daemon=True)
-    helper.start()
-    ambiguous = 0
-    try:
-        for a, b in bounds:
-            values, stats = engine.predict_host_values(dm, arr[a:b], dm.classes_f64, exact=_exact_default())
-            ambiguous += int(stats.get("n_ambiguous", 0))
-            work.put((a, b, values))
-    finally:
-        work.put(None)
-        helper.join()
-    if failure:
-        raise failure[0]
-    _note_ambiguous({"n_ambiguous": ambiguous})
-    return out
+#: from this many rows on, the list of the predictor contract is built piecewise while the batch is still in flight
+_ASYNC_LIST_MIN_ROWS = 1_000_000
 
 
 def linear_predict_proba(estimator: Any, features: Any) -> np.ndarray:
