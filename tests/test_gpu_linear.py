@@ -137,9 +137,10 @@ def test_layouts_and_dtypes(engine, digits_model):
         np.testing.assert_array_equal(got2, w, err_msg=name)
 
 
-def test_inline_and_list_rescore_agree(engine, digits_model):
-    """UML_B200_INLINE_RESCORE=1 re-scores flagged rows inside the tile kernel (kept as an A/B switch: it lost the same-box
-    comparison, profiles/r02_ab.json); the default is the flag list + rescore_f64_kernel.  Same labels, same counters."""
+def test_queue_and_kernel_rescore_agree(engine, digits_model):
+    """UML_B200_RESCORE_MODE=queue: flagged rows go through a shared-memory queue to a re-score warp of the tile kernel
+    (one launch); =kernel: flag list + rescore_f64_kernel (two launches).  Same labels, same counters - also when most
+    rows are near-ties and the queue backs up (the scoring warps then re-score their own rows)."""
     import os
     import subprocess
     import sys
@@ -153,15 +154,22 @@ def test_inline_and_list_rescore_agree(engine, digits_model):
         "X = np.random.default_rng(31).integers(0, 17, size=(1_500_000, 64), dtype=np.uint8).astype(np.float32)\n"
         "idx, st = e.predict(m, e.stage(X), exact=True)\n"
         "print(st['kernel_launches'], st['n_flagged'], int(idx.astype(np.int64).sum()), int((idx * np.arange(idx.size) %% 1000003).sum()))\n"
+        "m0 = e.load_linear(np.zeros((5, 64)), np.zeros(5))   # every row is a five-way tie: all rows flagged\n"
+        "idx0, st0 = e.predict(m0, e.stage(X[:300_000]), exact=True)\n"
+        "print(st0['n_flagged'], st0['n_ambiguous'], int(idx0.sum()))\n"
+        "u8 = e.device_alloc(300_000); e.predict_peers(m0, e.stage(X[:300_000]), [u8.ptr], 0, exact=True, want_stats=True, label_bytes=1)\n"
+        "print(int(e.take_labels(u8.ptr, 300_000, np.arange(5.0), label_bytes=1).sum()))\n"
     ) % (str(root), str(root / "tests" / "golden" / "digits_lr.npz"))
     outs = []
-    for flag in ("1", "0"):
-        env = dict(os.environ, UML_B200_INLINE_RESCORE=flag)
+    for mode in ("queue", "kernel"):
+        env = dict(os.environ, UML_B200_RESCORE_MODE=mode)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(r.stdout.split())
-    assert outs[0][0] == "1" and outs[1][0] == "2"   # one launch inline, two with the flag list
-    assert outs[0][1:] == outs[1][1:] and int(outs[0][1]) > 0
+        outs.append([ln.split() for ln in r.stdout.strip().splitlines()])
+    assert outs[0][0][0] == "1" and outs[1][0][0] == "2"   # one launch with the queue, two with the flag list
+    assert outs[0][0][1:] == outs[1][0][1:] and int(outs[0][0][1]) > 0
+    assert outs[0][1] == outs[1][1] == ["300000", "300000", "0"]   # all flagged, all ambiguous, first index wins
+    assert outs[0][2] == outs[1][2] == ["0"]
 
 
 def test_lossy_float64_features_use_the_f64_copy(engine):

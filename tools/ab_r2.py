@@ -1,5 +1,6 @@
 """Same-box A/B runs (box-to-box variation on this pool is ~10 %, so only same-call comparisons count):
-  * linear step with the fp64 re-score inline (default) vs as a second kernel (UML_B200_INLINE_RESCORE=0), 10M and 1.25M rows
+  * linear step: default (flag list + PDL-launched re-score kernel) vs re-score inside the tile kernel
+    (UML_B200_RESCORE_MODE=queue: shared-memory queue + re-score warp) vs plain launches (UML_B200_NO_PDL=1), 10M and 1.25M rows
   * MLP step: tensor-core kernel vs CUDA-core kernel (UML_B200_MLP_TC=0)
 Each variant runs in its own process (the switches are read once).  Prints one JSON object."""
 import json
@@ -49,8 +50,9 @@ def run(what, rows, env):
 
 out = {}
 for rows in (10_000_000, 1_250_000):
-    out[f"linear_{rows}"] = {"inline": run("linear", rows, {}), "second_kernel": run("linear", rows, {"UML_B200_INLINE_RESCORE": "0"}),
-                             "inline_again": run("linear", rows, {})}
-out["mlp_10000000"] = {"tcgen05": run("mlp", 10_000_000, {}), "ffma": run("mlp", 10_000_000, {"UML_B200_MLP_TC": "0"})}
+    out[f"linear_{rows}"] = {"default": run("linear", rows, {}), "queue_rescore": run("linear", rows, {"UML_B200_RESCORE_MODE": "queue"}),
+                             "no_pdl": run("linear", rows, {"UML_B200_NO_PDL": "1"}), "default_again": run("linear", rows, {})}
+out["mlp_10000000"] = {"tcgen05": run("mlp", 10_000_000, {}), "tcgen05_no_pdl": run("mlp", 10_000_000, {"UML_B200_NO_PDL": "1"}),
+                       "ffma": run("mlp", 10_000_000, {"UML_B200_MLP_TC": "0"})}
 out["mlp_1250000"] = {"tcgen05": run("mlp", 1_250_000, {}), "ffma": run("mlp", 1_250_000, {"UML_B200_MLP_TC": "0"})}
 print(json.dumps(out, indent=1))

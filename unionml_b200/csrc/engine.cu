@@ -856,7 +856,7 @@ static int enqueue_predict(uml_engine* e, const uml_model* m, const LinearLaunch
     *launches += 1;
     *path = 1;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
-    if (need_rescore) {  // only with UML_B200_INLINE_RESCORE=0: flagged rows are otherwise re-scored inside the tile kernel
+    if (need_rescore) {  // UML_B200_RESCORE_MODE=kernel; in queue mode flagged rows are re-scored by a warp of the tile kernel
       NvtxRange r_rescore("uml:rescore_f64");
       UML_CUDA(e, uml::launch_rescore_f64(m->dm, l, fl, false, e->info.sm_count, e->stream));
       *launches += 1;

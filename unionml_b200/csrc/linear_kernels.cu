@@ -20,6 +20,10 @@
 #include "tma_ring.cuh"
 #include "rescore_util.cuh"
 
+#ifndef UML_RESCORE_QUEUE_DEFAULT
+#define UML_RESCORE_QUEUE_DEFAULT 0
+#endif
+
 
 namespace uml {
 
@@ -120,8 +124,8 @@ struct TmaKernelParams {
   int* flag_count;
   int32_t* flag_rows;
   int flag_cap;
-  // INLINE re-score (EXACT kernels): a flagged row is re-scored in fp64 by its own warp right in the epilogue - no flag
-  // list, no second kernel launch behind every step
+  // QUEUE kernels (EXACT): flagged rows are re-scored in fp64 by a dedicated warp of the same launch - no flag list in
+  // global memory, no second kernel behind every step
   const float* x;
   const double* x64;
   SrcView src;
@@ -152,8 +156,21 @@ __device__ __noinline__ int rescore_row_inline(const TmaKernelParams& p, long lo
   return r.idx;
 }
 
-template <int C, bool EXACT, bool INLINE>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kQueueCap = 2048;           // flagged-row queue of the QUEUE kernels (power of two)
+constexpr int kQueueHeadroom = 1024;      // a warp publishes only while this many slots are free (8 warps x 128 rows)
+constexpr int kThreadsQueue = kThreads + 32;  // + 1 fp64 re-score warp
+
+// the final label of a re-scored row into every target the launch writes (one lane)
+__device__ __forceinline__ void store_final_label(const TmaKernelParams& p, long long row, int idx) {
+  if (p.labels) p.labels[row] = idx;
+  for (int i = 0; i < p.n_peers; ++i) {
+    if (p.wire_u8) static_cast<uint8_t*>(p.peers[i])[p.row_offset + row] = static_cast<uint8_t>(idx);
+    else static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idx;
+  }
+}
+
+template <int C, bool EXACT, bool QUEUE>
+__global__ void __launch_bounds__(kThreadsQueue, 1)
 linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TmaKernelParams p) {
   constexpr int NCOL = C + (EXACT ? 1 : 0);  // accumulators per row (classes + error-bound column)
   constexpr int CP = (C + 1 + 3) / 4 * 4;    // padded columns of wt in shared memory (layout shared by both modes)
@@ -169,6 +186,10 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
   float* bias_s = wt_s + p.f_pad * CP;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + CP);
   uint64_t* empty_bar = full_bar + S;
+  // QUEUE kernels: rows flagged by the scoring warps travel through this shared-memory queue to the re-score warp
+  // (slot value = row + 1, 0 = empty); ctl[0] = tail (reserved), ctl[1] = head (consumed), ctl[2] = scoring warps done
+  int* q_slots = reinterpret_cast<int*>(empty_bar + S);
+  int* q_ctl = q_slots + kQueueCap;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,8 +199,11 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
     const float4* src = reinterpret_cast<const float4*>(p.wt);
     float4* dst = reinterpret_cast<float4*>(wt_s);
     const int n4 = p.f_pad * CP / 4;
-    for (int i = threadIdx.x; i < n4; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
     if (threadIdx.x < CP) bias_s[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+    if constexpr (QUEUE) {
+      for (int i = threadIdx.x; i < kQueueCap + 4; i += blockDim.x) q_slots[i] = 0;
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -221,13 +245,14 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
       }
     }
   } else {
-    // ===================== consumers: one 128-row tile per warp at a time =====================
+    // ===================== consumers: one 128-row tile per warp at a time (warp 9 of the QUEUE kernels: re-score) ====
+    const bool scoring_warp = warp < kConsumerWarps;
     // lane l owns rows l, l+32, l+64, l+96 of the tile.  Row r of a box sits at byte r*128 with its 16-byte chunks
     // XOR-swizzled by (r & 7); r & 7 == l & 7 for all four rows, so one swizzle term serves them all and the eight
     // lanes of every LDS.128 phase hit eight distinct bank groups.
     const uint32_t lanebase = static_cast<uint32_t>(lane) * 128u + static_cast<uint32_t>(lane & 7) * 16u;
     uint32_t seq_base = 0;
-    for (long long first = blockIdx.x; first < num_tiles; first += G * kConsumerWarps) {
+    for (long long first = blockIdx.x; scoring_warp && first < num_tiles; first += G * kConsumerWarps) {
       const int nv = static_cast<int>(min(static_cast<long long>(kConsumerWarps), (num_tiles - first + G - 1) / G));
       if (warp < nv) {
         const long long tile = first + warp * G;
@@ -340,22 +365,6 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
           // certain iff margin > 2 * err, err <= (F+4) 2^-24 A; NaN/Inf anywhere makes the comparison false
           flag[j] = EXACT && row < p.n_rows && !((best - second) > p.thr * acc[j][C]);
         }
-        if constexpr (EXACT && INLINE) {
-          // re-score the (rare) flagged rows now, warp-wide in fp64, so the labels below are final
-          int n_flag = 0;
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            unsigned mask = __ballot_sync(0xffffffffu, flag[j]);
-            n_flag += __popc(mask);
-            while (mask != 0u) {
-              const int l = __ffs(static_cast<int>(mask)) - 1;
-              mask &= mask - 1u;
-              const int idx64 = rescore_row_inline(p, row0 + l + 32 * j, lane);
-              if (lane == l) idxs[j] = idx64;
-            }
-          }
-          if (lane == 0 && n_flag > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n_flag));
-        }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const long long row = row0 + lane + 32 * j;
@@ -364,7 +373,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             if (!p.wire_u8)
               for (int i = 0; i < p.n_peers; ++i) static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idxs[j];
           }
-          if constexpr (EXACT && !INLINE) {
+          if constexpr (EXACT && !QUEUE) {
             const unsigned mask = __ballot_sync(0xffffffffu, flag[j]);
             if (mask != 0u) {
               int base = 0;
@@ -400,8 +409,102 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
                   static_cast<uint8_t*>(p.peers[i])[at + t] = static_cast<uint8_t>((word >> (8 * t)) & 0xffu);
           }
         }
+        if constexpr (EXACT && QUEUE) {
+          // hand the (rare) flagged rows to the re-score warp: the labels above are provisional for them
+          unsigned masks[R];
+          int total = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            masks[j] = __ballot_sync(0xffffffffu, flag[j]);
+            total += __popc(masks[j]);
+          }
+          if (total > 0) {
+            __threadfence();  // the provisional labels are visible before the re-score warp may overwrite them
+            int base = -1;
+            if (lane == 0) {
+              const int tail = *reinterpret_cast<volatile int*>(&q_ctl[0]);
+              const int head = *reinterpret_cast<volatile int*>(&q_ctl[1]);
+              if (tail - head <= kQueueCap - kQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= 0) {
+              int off = base;
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                if (flag[j]) {
+                  const int slot = (off + __popc(masks[j] & ((1u << lane) - 1u))) & (kQueueCap - 1);
+                  *reinterpret_cast<volatile int*>(&q_slots[slot]) = static_cast<int>(row0 + lane + 32 * j) + 1;
+                }
+                off += __popc(masks[j]);
+              }
+            } else {
+              // the queue is backed up (most rows of the batch are near-ties): this warp re-scores its own rows, which
+              // keeps the worst case at "every warp does fp64" instead of "every warp waits for one"
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                unsigned mask = masks[j];
+                while (mask != 0u) {
+                  const int l = __ffs(static_cast<int>(mask)) - 1;
+                  mask &= mask - 1u;
+                  const long long row = row0 + l + 32 * j;
+                  const int idx64 = rescore_row_inline(p, row, lane);
+                  if (lane == 0) store_final_label(p, row, idx64);
+                }
+              }
+              if (lane == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(total));
+            }
+          }
+        }
       }
       seq_base += static_cast<uint32_t>(KC * nv);
+    }
+    if constexpr (EXACT && QUEUE) {
+      if (warp < kConsumerWarps) {
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          atomicAdd(&q_ctl[2], 1);  // this scoring warp has published everything it will ever publish
+        }
+      }
+    }
+    if constexpr (EXACT && QUEUE) {
+      if (warp == kConsumerWarps + 1) {
+        // ===================== fp64 re-score warp: drains the queue while the scoring warps stream =====================
+        int t = 0;
+        for (;;) {
+          // lane 0 looks at the queue and broadcasts what it saw: the lanes of a warp need not run in lockstep, so
+          // thirty-two separate volatile reads could disagree about a slot that is being published
+          int v = 0, state = 0;  // state: 1 = done, nothing left; 2 = idle, poll again after a short sleep
+          if (lane == 0) {
+            v = *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]);
+            if (v == 0) {
+              if (*reinterpret_cast<volatile int*>(&q_ctl[2]) == kConsumerWarps) {
+                __threadfence_block();
+                state = (t == *reinterpret_cast<volatile int*>(&q_ctl[0])) ? 1 : 0;  // 0: published, read the slot again
+              } else {
+                state = 2;
+              }
+            }
+          }
+          v = __shfl_sync(0xffffffffu, v, 0);
+          state = __shfl_sync(0xffffffffu, state, 0);
+          if (v == 0) {
+            if (state == 1) break;
+            if (state == 2) __nanosleep(200);
+            continue;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]) = 0;
+            *reinterpret_cast<volatile int*>(&q_ctl[1]) = t + 1;
+          }
+          ++t;
+          const long long row = static_cast<long long>(v) - 1;
+          const int idx64 = rescore_row_inline(p, row, lane);
+          if (lane == 0) store_final_label(p, row, idx64);
+        }
+        if (lane == 0 && t > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(t));
+      }
     }
   }
 }
@@ -626,8 +729,8 @@ cudaError_t launch_linear_proba(const LinearDeviceModel& m, const float* x, int6
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static size_t tma_fixed_smem(const LinearDeviceModel& m) {
-  // alignment slack + W^T + bias + barriers (64 stages max)
-  return 1024 + static_cast<size_t>(m.f_pad) * m.cp * 4 + static_cast<size_t>(m.cp) * 4 + 2 * 64 * 8;
+  // alignment slack + W^T + bias + barriers (64 stages max) + the flagged-row queue of the QUEUE kernels
+  return 1024 + static_cast<size_t>(m.f_pad) * m.cp * 4 + static_cast<size_t>(m.cp) * 4 + 2 * 64 * 8 + (kQueueCap + 4) * 4;
 }
 
 bool linear_tma_supported(const LinearDeviceModel& m, std::string* why) {
@@ -643,27 +746,27 @@ bool linear_tma_supported(const LinearDeviceModel& m, std::string* why) {
   return true;
 }
 
-template <int C, bool EXACT, bool INLINE>
+template <int C, bool EXACT, bool QUEUE>
 static cudaError_t launch_one(const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
                               cudaStream_t stream) {
-  auto kern = linear_argmax_tma_kernel<C, EXACT, INLINE>;
+  auto kern = linear_argmax_tma_kernel<C, EXACT, QUEUE>;
   static size_t configured = 0;  // per instantiation (one device per process): set the attribute once, not per launch
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  kern<<<grid, kThreads, smem, stream>>>(xmap, p);
+  kern<<<grid, QUEUE ? kThreadsQueue : kThreads, smem, stream>>>(xmap, p);
   return cudaGetLastError();
 }
 
-template <bool EXACT, bool INLINE>
+template <bool EXACT, bool QUEUE>
 static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKernelParams& p, int grid, size_t smem,
                                     cudaStream_t stream) {
   switch (C) {
 #define UML_CASE(N) \
   case N:           \
-    return launch_one<N, EXACT, INLINE>(xmap, p, grid, smem, stream);
+    return launch_one<N, EXACT, QUEUE>(xmap, p, grid, smem, stream);
     UML_CASE(2) UML_CASE(3) UML_CASE(4) UML_CASE(5) UML_CASE(6) UML_CASE(7) UML_CASE(8) UML_CASE(9) UML_CASE(10)
     UML_CASE(11) UML_CASE(12) UML_CASE(13) UML_CASE(14) UML_CASE(15) UML_CASE(16)
 #undef UML_CASE
@@ -672,19 +775,23 @@ static cudaError_t dispatch_classes(int C, const CUtensorMap& xmap, const TmaKer
   }
 }
 
-bool linear_inline_rescore_default() {
-  // Default OFF.  Re-scoring a flagged row inside the tile kernel (by its own warp, right in the epilogue) removes the
-  // second launch but lost the same-box A/B of round 2: 10M rows 0.397 vs 0.375 ms per step, 1.25M rows 70.1 vs
-  // 65.7 us (profiles/r02_ab.json) - the extra ballots and the out-of-line fp64 call cost every tile more than the
-  // launch they save.  UML_B200_INLINE_RESCORE=1 switches it on for re-measurement.
-  static const bool on = getenv("UML_B200_INLINE_RESCORE") && getenv("UML_B200_INLINE_RESCORE")[0] == '1';
-  return on;
+bool linear_queue_rescore() {
+  // UML_B200_RESCORE_MODE=queue: flagged rows go through a shared-memory queue to a tenth warp of the tile kernel that
+  // re-scores them in fp64 while the other warps keep streaming (one launch per step); =kernel: flag list in global
+  // memory + rescore_f64_kernel behind the tile kernel (two launches).  Default below, chosen by same-box A/B.
+  static const int mode = [] {
+    const char* env = getenv("UML_B200_RESCORE_MODE");
+    if (env && env[0] == 'q') return 1;
+    if (env && env[0] == 'k') return 0;
+    return UML_RESCORE_QUEUE_DEFAULT;
+  }();
+  return mode == 1;
 }
 
 cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
                               const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err,
                               bool* rescore_kernel_needed) {
-  const bool inline_rescore = exact && linear_inline_rescore_default();
+  const bool inline_rescore = exact && linear_queue_rescore();
   if (rescore_kernel_needed) *rescore_kernel_needed = exact && !inline_rescore;
   if (!linear_tma_supported(m, err)) return cudaErrorInvalidValue;
   if (l.n_rows <= 0) return cudaSuccess;

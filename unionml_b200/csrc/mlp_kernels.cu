@@ -95,6 +95,7 @@ mlp_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const MlpKernelP
   }
   __syncthreads();
 
+  pdl_launch_dependents();  // see linear_kernels.cu: the re-score kernel may be scheduled while this grid drains
   const long long G = gridDim.x;
   const long long num_tiles = p.num_tiles;
   const int KC = p.kc;
