@@ -50,9 +50,10 @@ def run(what, rows, env):
 
 out = {}
 for rows in (10_000_000, 1_250_000):
-    out[f"linear_{rows}"] = {"default": run("linear", rows, {}), "queue_rescore": run("linear", rows, {"UML_B200_RESCORE_MODE": "queue"}),
+    out[f"linear_{rows}"] = {"default": run("linear", rows, {}), "rescore_kernel": run("linear", rows, {"UML_B200_RESCORE_MODE": "kernel"}),
                              "no_pdl": run("linear", rows, {"UML_B200_NO_PDL": "1"}), "default_again": run("linear", rows, {})}
-out["mlp_10000000"] = {"tcgen05": run("mlp", 10_000_000, {}), "tcgen05_no_pdl": run("mlp", 10_000_000, {"UML_B200_NO_PDL": "1"}),
+out["mlp_10000000"] = {"tcgen05": run("mlp", 10_000_000, {}), "tcgen05_rescore_kernel": run("mlp", 10_000_000, {"UML_B200_MLP_RESCORE_MODE": "kernel"}),
                        "ffma": run("mlp", 10_000_000, {"UML_B200_MLP_TC": "0"})}
-out["mlp_1250000"] = {"tcgen05": run("mlp", 1_250_000, {}), "ffma": run("mlp", 1_250_000, {"UML_B200_MLP_TC": "0"})}
+out["mlp_1250000"] = {"tcgen05": run("mlp", 1_250_000, {}), "tcgen05_rescore_kernel": run("mlp", 1_250_000, {"UML_B200_MLP_RESCORE_MODE": "kernel"}),
+                      "ffma": run("mlp", 1_250_000, {"UML_B200_MLP_TC": "0"})}
 print(json.dumps(out, indent=1))

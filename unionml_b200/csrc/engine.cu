@@ -1704,6 +1704,8 @@ static int mlp_predict_common(uml_engine* e, const uml_mlp* m, const uml_batch* 
   uml::MlpTcLaunch out{};
   out.n_rows = b->n_rows;
   out.row_offset = row_offset;
+  out.x = b->x;
+  out.ld = b->ld;
   const bool wire_u8 = n_peers > 0 && label_bytes == 1;
   out.wire_u8 = wire_u8 ? 1 : 0;
   int32_t* d_labels = labels_out;
@@ -1733,11 +1735,12 @@ static int mlp_predict_common(uml_engine* e, const uml_mlp* m, const uml_batch* 
   if (timed) UML_CUDA(e, cudaEventRecord(e->ev[1], e->stream));
   if (use_tc) {
     NvtxRange r_score("uml:mlp_score_tcgen05");
-    UML_CUDA(e, uml::launch_mlp_tc(b->map, m->dm, out, exact, fl, e->info.sm_count, e->stream));
+    bool need_rescore = false;
+    UML_CUDA(e, uml::launch_mlp_tc(b->map, m->dm, out, exact, fl, e->info.sm_count, e->stream, &need_rescore));
     launches += 1;
     path = 5;
     if (timed) UML_CUDA(e, cudaEventRecord(e->ev[2], e->stream));
-    if (exact) {
+    if (need_rescore) {  // UML_B200_MLP_RESCORE_MODE=kernel; in queue mode four warps of the scoring kernel do it
       NvtxRange r_rescore("uml:mlp_rescore_f64");
       UML_CUDA(e, uml::launch_mlp_rescore_f64(m->dm, b->x, b->ld, b->n_rows, out, fl, false, e->info.sm_count, e->stream));
       launches += 1;

@@ -19,7 +19,7 @@
 
 #include "uml_common.cuh"
 #include "tma_ring.cuh"
-#include "rescore_util.cuh"
+#include "mlp_rescore.cuh"
 
 #ifndef UML_MLP_UNROLL_Q
 #define UML_MLP_UNROLL_Q 8  // feature-quad unroll of the layer-1 loop (same-box A/B, EXACT: 1 -> 1.120, 2 -> 1.056, 4 -> 1.023, 8 -> 1.015 ms)
@@ -286,133 +286,37 @@ struct MlpRescoreParams {
   unsigned long long* counters;
 };
 
-// Shared-memory version: W1 (fp64, [F][H]), W2 ([C][H+1], padded rows) and the biases are staged once per block; per
-// row the warp loads x with one coalesced access, keeps it (as doubles) and the hidden activations in its own
-// shared-memory strip, and every inner-loop operand is a broadcast / conflict-free LDS.  Layer 1: lane per hidden
-// unit, four independent fp64 chains over the features.  Layer 2: lane per class (no warp reductions), then one
-// butterfly for arg-max and runner-up.  ~1 us per row instead of ~10 us for the global-memory loop this replaces.
+// Shared-memory version (mlp_rescore.cuh): W1 (fp64, [F][H]), W2 ([C][H+1], padded rows), the biases and two bound
+// vectors are staged once per block; per row the warp loads x with one coalesced access, keeps it (as doubles) and the
+// hidden activations in its own shared-memory strip, and every inner-loop operand is a broadcast / conflict-free LDS.
+// Layer 1: lane per hidden unit, four independent fp64 chains over the features.  Layer 2: lane per class (no warp
+// reductions), then one butterfly for arg-max and runner-up.
 __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
   extern __shared__ double rs_smem[];
   // (weights are staged first: they do not depend on the scoring kernel; the flag list does - see the wait below)
-  const int F = p.F, H = p.H, C = p.C;
-  const int HP = H + 1;
-  double* w1s = rs_smem;                 // [F][H]
-  double* w2s = w1s + F * H;             // [C][H + 1]
-  double* b1s = w2s + C * HP;            // [H]
-  double* b2s = b1s + H;                 // [C]
-  double* w1m = b2s + C;                 // [F]  max_n |w1_nf|
-  double* w2m = w1m + F;                 // [H]  max_c |w2_cn|
-  double* strips = w2m + H;              // per warp: xs[F] | hv[H]
+  const MlpRsView view = mlp_rs_stage(rs_smem, p.w1, p.b1, p.w2, p.b2, p.F, p.H, p.C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* xs = strips + warp * (F + H);
-  double* hv = xs + F;
-  for (int i = threadIdx.x; i < F * H; i += blockDim.x) w1s[i] = p.w1[i];
-  for (int i = threadIdx.x; i < C * H; i += blockDim.x) w2s[(i / H) * HP + (i % H)] = p.w2[i];
-  for (int i = threadIdx.x; i < H; i += blockDim.x) b1s[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = p.b2[i];
+  double* xs = rs_smem + mlp_rs_weight_doubles(p.F, p.H, p.C) + warp * mlp_rs_strip_doubles(p.F, p.H);
+  double* hv = xs + p.F;
   __syncthreads();
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    double m = 0.0;
-    for (int hn = 0; hn < H; ++hn) m = fmax(m, fabs(w1s[f * H + hn]));
-    w1m[f] = m;
-  }
-  for (int hn = threadIdx.x; hn < H; hn += blockDim.x) {
-    double m = 0.0;
-    for (int c = 0; c < C; ++c) m = fmax(m, fabs(w2s[c * HP + hn]));
-    w2m[hn] = m;
-  }
-  double b1max = 0.0, b2max = 0.0;
-  for (int hn = 0; hn < H; ++hn) b1max = fmax(b1max, fabs(b1s[hn]));
-  for (int c = 0; c < C; ++c) b2max = fmax(b2max, fabs(b2s[c]));
-  __syncthreads();
-  double w2sum = 0.0;  // sum_n max_c |w2_cn|: how far a hidden-layer error can move any logit
-  for (int hn = 0; hn < H; ++hn) w2sum += w2m[hn];
 
   pdl_wait_for_predecessor();  // from here on: the flag list and labels of the scoring kernel this launch depends on
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
   if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
-  const double u = 1.1102230246251565e-16;
   for (long long i = warp_global; i < n; i += warps_total) {
     const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
-    const float* xr = p.x + row * p.ld;
-    bool bad = false;
-    double a1 = 0.0;  // sum_f |x_f| max_n |w1_nf|: bounds every hidden unit's absolute sum (one chain instead of H)
-    for (int f = lane; f < F; f += 32) {
-      const float xf = xr[f];
-      bad |= !isfinite(xf);
-      const double xd = static_cast<double>(xf);
-      xs[f] = xd;
-      a1 = fma(fabs(xd), w1m[f], a1);
-    }
-    bad = __any_sync(0xffffffffu, bad);
-    a1 = warp_sum(a1) + b1max;
-    const double herr = (F + 6.0) * u * a1;  // any hidden unit's own fp64 rounding error (four partial chains + their sum)
-    __syncwarp();  // the strip writes above are read by other lanes below
-    // ---- hidden layer: lane per unit, four chains over the features ----
-    double a2 = 0.0;  // sum_n (h_n + herr) max_c |w2_cn|: bounds every logit's absolute sum
-    for (int hn = lane; hn < H; hn += 32) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int f = 0;
-      for (; f + 4 <= F; f += 4) {
-        s0 = fma(xs[f], w1s[f * H + hn], s0);
-        s1 = fma(xs[f + 1], w1s[(f + 1) * H + hn], s1);
-        s2 = fma(xs[f + 2], w1s[(f + 2) * H + hn], s2);
-        s3 = fma(xs[f + 3], w1s[(f + 3) * H + hn], s3);
-      }
-      for (; f < F; ++f) s0 = fma(xs[f], w1s[f * H + hn], s0);
-      const double h = fmax(((s0 + s1) + (s2 + s3)) + b1s[hn], 0.0);
-      hv[hn] = h;
-      a2 = fma(h, w2m[hn], a2);
-    }
-    const double amax = warp_sum(a2) + herr * w2sum + b2max;
-    __syncwarp();
-    // ---- output layer: lane per class ----
-    double best = 0.0, second = -INFINITY;
-    int idx = 0;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int c = c0 + lane;
-      double s0 = 0.0, s1 = 0.0;
-      if (c < C) {
-        const double* w2c = w2s + c * HP;
-        int nn = 0;
-        for (; nn + 2 <= H; nn += 2) {
-          s0 = fma(hv[nn], w2c[nn], s0);
-          s1 = fma(hv[nn + 1], w2c[nn + 1], s1);
-        }
-        for (; nn < H; ++nn) s0 = fma(hv[nn], w2c[nn], s0);
-      }
-      Top2 t;
-      t.best = c < C ? (s0 + s1) + b2s[c] : -INFINITY;
-      t.second = -INFINITY;
-      t.idx = c;
-      top2_butterfly(t, 1);
-      if (c0 == 0) {
-        best = t.best;
-        second = t.second;
-        idx = t.idx;
-      } else if (t.best > best) {
-        second = fmax(best, t.second);
-        best = t.best;
-        idx = t.idx;
-      } else {
-        second = fmax(second, t.best);
-      }
-    }
-    if (idx >= C) idx = 0;
+    const MlpRowResult r = mlp_rs_row(view, p.x + row * p.ld, xs, hv, lane);
     if (lane == 0) {
-      if (p.labels) p.labels[row] = idx;
+      if (p.labels) p.labels[row] = r.idx;
       for (int q = 0; q < p.n_peers; ++q) {
-        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(idx);
-        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = idx;
+        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(r.idx);
+        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = r.idx;
       }
-      if (bad) atomicAdd(&p.counters[1], 1ull);
-      // fp64 error of a logit: the hidden units' own errors carried through W2, plus the output layer's chain
-      const double err = herr * w2sum + (static_cast<double>(H) + 16.0) * u * amax;
-      if (!((best - second) > 2.0 * err)) atomicAdd(&p.counters[0], 1ull);
+      if (r.bad) atomicAdd(&p.counters[1], 1ull);
+      if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
     }
-    __syncwarp();  // the strip is reused by the next row
   }
   // hand the flag list back empty (see rescore_f64_kernel in linear_kernels.cu)
   __syncthreads();
@@ -531,8 +435,7 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   p.row_offset = out.row_offset;
   p.counters = flags.counters;
   // shared memory: W1 + padded W2 + biases + the two bound vectors + one strip (x, hidden values) per warp
-  const size_t F = m.n_in, H = m.n_hidden, C = m.n_classes;
-  const size_t smem = (F * H + C * (H + 1) + H + C + F + H + 8 * (F + H)) * sizeof(double);
+  const size_t smem = (mlp_rs_weight_doubles(m.n_in, m.n_hidden, m.n_classes) + 8 * mlp_rs_strip_doubles(m.n_in, m.n_hidden)) * sizeof(double);
   if (smem > static_cast<size_t>(kMaxSmemBytes)) return cudaErrorInvalidValue;  // uml_mlp_load bounds F * H
   static size_t configured = 0;
   if (smem > configured) {

@@ -35,14 +35,27 @@
 
 #include "uml_common.cuh"
 #include "tcgen05.cuh"
+#include "mlp_rescore.cuh"
+
+#ifndef UML_MLP_QUEUE_DEFAULT
+#define UML_MLP_QUEUE_DEFAULT 1
+#endif
 
 namespace uml {
 
 constexpr int kTcThreads = 448;
 constexpr int kTcProducerWarp = 12;
 constexpr int kTcMmaWarp = 13;
+// QUEUE kernels: rows flagged by the epilogue warps are re-scored in fp64 by four more warps of the same launch while
+// the tensor-core pipeline keeps streaming (fp64 units and these issue slots are otherwise idle)
+constexpr int kTcRescoreWarps = 4;
+constexpr int kTcFirstRescoreWarp = 14;
+constexpr int kTcThreadsQueue = kTcThreads + 32 * kTcRescoreWarps;
+constexpr int kTcEpilogueWarps = 8;
+constexpr int kTcQueueCap = 1024;       // power of two
+constexpr int kTcQueueHeadroom = 512;   // a warp publishes only while this many slots are free (8 warps x 32 rows at once)
 constexpr int kTcAccStages = 4;    // TMEM accumulator stages (tiles in flight between MMA and epilogue)
-constexpr int kTcSlots = 32;       // A1 hand-off slots (scan -> epilogue); > the scan warps' maximum lead over the epilogue
+constexpr int kTcSlots = 24;       // A1 hand-off slots (scan -> epilogue); > the scan warps' maximum lead over the epilogue
 constexpr int kTcMaxFpad = 128;    // features (padded to 32) the resident W1 tile is sized for
 
 template <int H, int C>
@@ -67,10 +80,28 @@ struct MlpTcParams {
   int* flag_count;
   int32_t* flag_rows;
   int flag_cap;
+  // QUEUE kernels: what the in-kernel fp64 re-score needs
+  const float* x;
+  long long ld;
+  int n_in;
+  const double* w1_64;  // [F][H]
+  const double* b1_64;
+  const double* w2_64;  // [C][H]
+  const double* b2_64;
+  unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] re-scored rows
 };
 
-template <int H, int C, bool EXACT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int H, int C>
+__device__ __forceinline__ void tc_store_final_label(const MlpTcParams<H, C>& p, long long row, int idx) {
+  if (p.labels) p.labels[row] = idx;
+  for (int i = 0; i < p.n_peers; ++i) {
+    if (p.wire_u8) static_cast<uint8_t*>(p.peers[i])[p.row_offset + row] = static_cast<uint8_t>(idx);
+    else static_cast<int32_t*>(p.peers[i])[p.row_offset + row] = idx;
+  }
+}
+
+template <int H, int C, bool EXACT, bool QUEUE>
+__global__ void __launch_bounds__(kTcThreadsQueue, 1)
 mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ MlpTcParams<H, C> p) {
   constexpr int N = 2 * H;  // accumulator columns per tile: [main | small]
   constexpr int TMEM_COLS = kTcAccStages * N;
@@ -92,6 +123,11 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   uint64_t* dempty_bar = dfull_bar + kTcAccStages;
   uint64_t* a1_bar = dempty_bar + kTcAccStages;
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(a1_bar + kTcSlots);
+  // QUEUE kernels: flagged-row queue (slot = row + 1, 0 = empty; ctl: 0 tail reserved, 1 head claimed, 2 epilogue
+  // warps done, 3 slots consumed), then the fp64 weights and one strip per epilogue / re-score warp
+  int* q_slots = reinterpret_cast<int*>(tmem_base_s + 4);
+  int* q_ctl = q_slots + kTcQueueCap;
+  double* rs_area = reinterpret_cast<double*>(q_ctl + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,8 +137,14 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     const float4* src = reinterpret_cast<const float4*>(p.w1_tiles);
     float4* dst = reinterpret_cast<float4*>(btile);
     const int n4 = KC * N * 32 / 4;
-    for (int i = threadIdx.x; i < n4; i += kTcThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
   }
+  MlpRsView rs_view{};
+  if constexpr (EXACT && QUEUE) {
+    for (int i = threadIdx.x; i < kTcQueueCap + 4; i += blockDim.x) q_slots[i] = 0;
+    rs_view = mlp_rs_stage(rs_area, p.w1_64, p.b1_64, p.w2_64, p.b2_64, p.n_in, H, C);
+  }
+  double* rs_strips = rs_area + mlp_rs_weight_doubles(p.n_in, H, C);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -215,7 +257,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&a1_bar[slot]);
     }
-  } else {
+  } else if (warp < 4 + kTcEpilogueWarps) {
     // ===================== epilogue warps 4..11: TMEM lane = row; set 0 (warps 4-7) even tiles, set 1 odd tiles ====
     const int wq = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
     const int set = (warp - 4) >> 2;
@@ -301,15 +343,102 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         const bool flagged = in_range && !certain;
         const unsigned mask = __ballot_sync(0xffffffffu, flagged);
         if (mask != 0u) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(p.flag_count, __popc(mask));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (flagged) {
-            const int pos = base + __popc(mask & ((1u << lane) - 1u));
-            if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
+          if constexpr (QUEUE) {
+            // hand the flagged rows to the re-score warps of this launch; the labels stored above are provisional
+            __threadfence();
+            const int total = __popc(mask);
+            int base = -1;
+            if (lane == 0) {
+              const int tail = *reinterpret_cast<volatile int*>(&q_ctl[0]);
+              const int consumed = *reinterpret_cast<volatile int*>(&q_ctl[3]);
+              if (tail - consumed <= kTcQueueCap - kTcQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= 0) {
+              if (flagged) {
+                const int slot = (base + __popc(mask & ((1u << lane) - 1u))) & (kTcQueueCap - 1);
+                volatile int* sp = reinterpret_cast<volatile int*>(&q_slots[slot]);
+                while (*sp != 0) {  // only if a consumer claimed this slot's previous ticket and has not read it yet
+                }
+                *sp = static_cast<int>(row) + 1;
+              }
+            } else {
+              // queue backed up (most rows near-ties): this warp re-scores its own rows in fp64
+              double* xs = rs_strips + (warp - 4) * mlp_rs_strip_doubles(p.n_in, H);
+              unsigned m2 = mask;
+              while (m2 != 0u) {
+                const int l = __ffs(static_cast<int>(m2)) - 1;
+                m2 &= m2 - 1u;
+                const long long frow = tile * kTileRows + wq * 32 + l;
+                const MlpRowResult r = mlp_rs_row(rs_view, p.x + frow * p.ld, xs, xs + p.n_in, lane);
+                if (lane == 0) {
+                  tc_store_final_label(p, frow, r.idx);
+                  if (r.bad) atomicAdd(&p.counters[1], 1ull);
+                  if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
+                }
+              }
+              if (lane == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(total));
+            }
+          } else {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.flag_count, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (flagged) {
+              const int pos = base + __popc(mask & ((1u << lane) - 1u));
+              if (pos < p.flag_cap) p.flag_rows[pos] = static_cast<int32_t>(row);
+            }
           }
         }
       }
+    }
+    if constexpr (EXACT && QUEUE) {
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(&q_ctl[2], 1);  // this epilogue warp has published everything it will ever publish
+      }
+    }
+  } else {
+    // ===================== re-score warps 14..17 (QUEUE kernels): fp64 rows from the queue =====================
+    if constexpr (EXACT && QUEUE) {
+      double* xs = rs_strips + (kTcEpilogueWarps + (warp - kTcFirstRescoreWarp)) * mlp_rs_strip_doubles(p.n_in, H);
+      int n_done = 0;
+      for (;;) {
+        // claim the next ticket, then wait until its slot is published (lane 0 polls and broadcasts: the lanes of a
+        // warp need not run in lockstep)
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&q_ctl[1], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        int v = 0;
+        for (;;) {
+          int state = 0;  // 1: nothing will ever be published for this ticket
+          if (lane == 0) {
+            v = *reinterpret_cast<volatile int*>(&q_slots[t & (kTcQueueCap - 1)]);
+            if (v == 0 && *reinterpret_cast<volatile int*>(&q_ctl[2]) == kTcEpilogueWarps) {
+              __threadfence_block();
+              if (t >= *reinterpret_cast<volatile int*>(&q_ctl[0])) state = 1;
+            }
+          }
+          v = __shfl_sync(0xffffffffu, v, 0);
+          state = __shfl_sync(0xffffffffu, state, 0);
+          if (v != 0 || state == 1) break;
+          __nanosleep(200);
+        }
+        if (v == 0) break;
+        if (lane == 0) {
+          *reinterpret_cast<volatile int*>(&q_slots[t & (kTcQueueCap - 1)]) = 0;
+          atomicAdd(&q_ctl[3], 1);
+        }
+        const long long frow = static_cast<long long>(v) - 1;
+        const MlpRowResult r = mlp_rs_row(rs_view, p.x + frow * p.ld, xs, xs + p.n_in, lane);
+        if (lane == 0) {
+          tc_store_final_label(p, frow, r.idx);
+          if (r.bad) atomicAdd(&p.counters[1], 1ull);
+          if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
+        }
+        ++n_done;
+      }
+      if (lane == 0 && n_done > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n_done));
     }
   }
 
@@ -355,9 +484,27 @@ std::vector<float> mlp_tc_build_w1_tiles(const float* w1 /*[H][F]*/, int H, int 
   return tiles;
 }
 
-static size_t mlp_tc_fixed_smem(const MlpDeviceModel& m) {
+static size_t mlp_tc_fixed_smem(const MlpDeviceModel& m, bool queue) {
   const size_t kc = m.f_pad / kChunkF;
-  return 1024 + kc * (2 * m.n_hidden) * 128 + static_cast<size_t>(kTcSlots) * kTileRows * 4 + (2 * 64 + 2 * kTcAccStages + kTcSlots) * 8 + 16;
+  size_t bytes = 1024 + kc * (2 * m.n_hidden) * 128 + static_cast<size_t>(kTcSlots) * kTileRows * 4 +
+                 (2 * 64 + 2 * kTcAccStages + kTcSlots) * 8 + 16;
+  if (queue)  // flagged-row queue + fp64 weights + one strip per epilogue / re-score warp
+    bytes += (kTcQueueCap + 4) * 4 + 16 +
+             (mlp_rs_weight_doubles(m.n_in, m.n_hidden, m.n_classes) +
+              (kTcEpilogueWarps + kTcRescoreWarps) * mlp_rs_strip_doubles(m.n_in, m.n_hidden)) * 8;
+  return bytes;
+}
+
+bool mlp_tc_queue_rescore() {
+  // UML_B200_MLP_RESCORE_MODE=queue: rows flagged by the epilogue go through a shared-memory queue to four fp64
+  // re-score warps of the same launch; =kernel: flag list + mlp_rescore_f64_kernel behind the scoring kernel
+  static const int mode = [] {
+    const char* env = getenv("UML_B200_MLP_RESCORE_MODE");
+    if (env && env[0] == 'q') return 1;
+    if (env && env[0] == 'k') return 0;
+    return UML_MLP_QUEUE_DEFAULT;
+  }();
+  return mode == 1;
 }
 
 bool mlp_tc_supported(const MlpDeviceModel& m, std::string* why) {
@@ -370,10 +517,10 @@ bool mlp_tc_supported(const MlpDeviceModel& m, std::string* why) {
     if (why) *why = "more than 128 features: the resident W1 tile is sized for F_pad <= 128";
     return false;
   }
-  return mlp_tc_fixed_smem(m) + 4 * static_cast<size_t>(kStageBytes) <= static_cast<size_t>(kMaxSmemBytes);
+  return mlp_tc_fixed_smem(m, true) + 6 * static_cast<size_t>(kStageBytes) <= static_cast<size_t>(kMaxSmemBytes);
 }
 
-template <int H, int C, bool EXACT>
+template <int H, int C, bool EXACT, bool QUEUE>
 static cudaError_t mlp_tc_launch_one(const CUtensorMap& xmap, const MlpDeviceModel& m, const MlpTcLaunch& l,
                                      const FlagList& flags, int sm_count, cudaStream_t stream) {
   using Params = MlpTcParams<H, C>;
@@ -417,7 +564,15 @@ static cudaError_t mlp_tc_launch_one(const CUtensorMap& xmap, const MlpDeviceMod
   p.n_rows = l.n_rows;
   p.num_tiles = (l.n_rows + kTileRows - 1) / kTileRows;
   p.kc = m.f_pad / kChunkF;
-  const size_t fixed = mlp_tc_fixed_smem(m);
+  p.x = l.x;
+  p.ld = l.ld;
+  p.n_in = m.n_in;
+  p.w1_64 = m.w1_64;
+  p.b1_64 = m.b1_64;
+  p.w2_64 = m.w2_64;
+  p.b2_64 = m.b2_64;
+  p.counters = flags.counters;
+  const size_t fixed = mlp_tc_fixed_smem(m, QUEUE);
   int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kStageBytes);
   stages = std::min(stages, 64);
   if (const char* env = getenv("UML_B200_STAGES")) stages = std::max(4, std::min(stages, atoi(env)));
@@ -428,7 +583,7 @@ static cudaError_t mlp_tc_launch_one(const CUtensorMap& xmap, const MlpDeviceMod
   p.flag_rows = flags.rows;
   p.flag_cap = flags.capacity;
   const size_t smem = fixed + static_cast<size_t>(stages) * kStageBytes;
-  auto kern = mlp_argmax_tc_kernel<H, C, EXACT>;
+  auto kern = mlp_argmax_tc_kernel<H, C, EXACT, QUEUE>;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -436,17 +591,21 @@ static cudaError_t mlp_tc_launch_one(const CUtensorMap& xmap, const MlpDeviceMod
     configured = smem;
   }
   const int grid = static_cast<int>(std::min<long long>(sm_count, std::max<long long>(1, p.num_tiles)));
-  kern<<<grid, kTcThreads, smem, stream>>>(xmap, p);
+  kern<<<grid, QUEUE ? kTcThreadsQueue : kTcThreads, smem, stream>>>(xmap, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mlp_tc(const CUtensorMap& xmap, const MlpDeviceModel& m, const MlpTcLaunch& l, bool exact,
-                          const FlagList& flags, int sm_count, cudaStream_t stream) {
+                          const FlagList& flags, int sm_count, cudaStream_t stream, bool* rescore_kernel_needed) {
+  const bool queue = exact && mlp_tc_queue_rescore();
+  if (rescore_kernel_needed) *rescore_kernel_needed = exact && !queue;
   if (l.n_rows <= 0) return cudaSuccess;
-#define UML_TC_CASE(HH, CC)                                                                              \
-  if (m.n_hidden == HH && m.n_classes == CC)                                                             \
-    return exact ? mlp_tc_launch_one<HH, CC, true>(xmap, m, l, flags, sm_count, stream)                  \
-                 : mlp_tc_launch_one<HH, CC, false>(xmap, m, l, flags, sm_count, stream);
+#define UML_TC_CASE(HH, CC)                                                                                      \
+  if (m.n_hidden == HH && m.n_classes == CC) {                                                                   \
+    if (!exact) return mlp_tc_launch_one<HH, CC, false, false>(xmap, m, l, flags, sm_count, stream);             \
+    return queue ? mlp_tc_launch_one<HH, CC, true, true>(xmap, m, l, flags, sm_count, stream)                    \
+                 : mlp_tc_launch_one<HH, CC, true, false>(xmap, m, l, flags, sm_count, stream);                  \
+  }
   UML_TC_CASE(32, 10) UML_TC_CASE(32, 2) UML_TC_CASE(32, 3) UML_TC_CASE(16, 10) UML_TC_CASE(16, 2) UML_TC_CASE(16, 3)
 #undef UML_TC_CASE
   return cudaErrorInvalidValue;

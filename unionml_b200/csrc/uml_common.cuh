@@ -138,6 +138,8 @@ struct MlpTcLaunch {
   int wire_u8;
   long long row_offset;
   long long n_rows;
+  const float* x;  // the batch rows (the in-kernel fp64 re-score of the tensor-core kernel reads flagged rows again)
+  long long ld;
 };
 bool mlp_tma_supported(const MlpDeviceModel& m, std::string* why);
 cudaError_t launch_mlp_tma(const CUtensorMap& xmap, const MlpDeviceModel& m, const float* x, int64_t n_rows,
@@ -148,7 +150,7 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
 bool mlp_tc_supported(const MlpDeviceModel& m, std::string* why);
 std::vector<float> mlp_tc_build_w1_tiles(const float* w1, int H, int F, int f_pad);
 cudaError_t launch_mlp_tc(const CUtensorMap& xmap, const MlpDeviceModel& m, const MlpTcLaunch& l, bool exact,
-                          const FlagList& flags, int sm_count, cudaStream_t stream);
+                          const FlagList& flags, int sm_count, cudaStream_t stream, bool* rescore_kernel_needed);
 // int32 labels (device) -> every target vector of a fused exchange (int32 or uint8 wire), for kernels without peer stores
 cudaError_t launch_labels_scatter(const int32_t* labels, int64_t n, void* const* peers, int n_peers, int wire_u8,
                                   int64_t row_offset, int sm_count, cudaStream_t stream);
