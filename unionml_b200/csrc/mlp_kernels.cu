@@ -294,10 +294,12 @@ struct MlpRescoreParams {
 __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
   extern __shared__ double rs_smem[];
   // (weights are staged first: they do not depend on the scoring kernel; the flag list does - see the wait below)
-  const MlpRsView view = mlp_rs_stage(rs_smem, p.w1, p.b1, p.w2, p.b2, p.F, p.H, p.C);
+  MlpRsView view = mlp_rs_stage(rs_smem, p.w1, p.b1, p.w2, p.b2, p.F, p.H, p.C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* xs = rs_smem + mlp_rs_weight_doubles(p.F, p.H, p.C) + warp * mlp_rs_strip_doubles(p.F, p.H);
   double* hv = xs + p.F;
+  __syncthreads();
+  mlp_rs_finish_stage(view);
   __syncthreads();
 
   pdl_wait_for_predecessor();  // from here on: the flag list and labels of the scoring kernel this launch depends on

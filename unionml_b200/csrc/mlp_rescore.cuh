@@ -25,8 +25,8 @@ __host__ __device__ inline size_t mlp_rs_weight_doubles(int F, int H, int C) {
 }
 __host__ __device__ inline size_t mlp_rs_strip_doubles(int F, int H) { return static_cast<size_t>(F) + H; }
 
-// all threads of the block: copy the fp64 weights from global memory and derive the bound vectors; returns the view
-// (the caller synchronises the block before the first row)
+// all threads of the block: copy the fp64 weights from global memory; returns the view.  After a block-wide barrier
+// every thread calls mlp_rs_finish_stage (bound vectors from the staged copies), then another barrier before rows.
 __device__ inline MlpRsView mlp_rs_stage(double* smem, const double* w1, const double* b1, const double* w2,
                                          const double* b2, int F, int H, int C) {
   const int HP = H + 1;
@@ -34,45 +34,50 @@ __device__ inline MlpRsView mlp_rs_stage(double* smem, const double* w1, const d
   double* w2s = w1s + F * H;
   double* b1s = w2s + C * HP;
   double* b2s = b1s + H;
-  double* w1m = b2s + C;
-  double* w2m = w1m + F;
   for (int i = threadIdx.x; i < F * H; i += blockDim.x) w1s[i] = w1[i];
   for (int i = threadIdx.x; i < C * H; i += blockDim.x) w2s[(i / H) * HP + (i % H)] = w2[i];
   for (int i = threadIdx.x; i < H; i += blockDim.x) b1s[i] = b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = b2[i];
-  // the bound vectors straight from global memory (no barrier needed before this point)
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    double m = 0.0;
-    for (int hn = 0; hn < H; ++hn) m = fmax(m, fabs(w1[f * H + hn]));
-    w1m[f] = m;
-  }
-  for (int hn = threadIdx.x; hn < H; hn += blockDim.x) {
-    double m = 0.0;
-    for (int c = 0; c < C; ++c) m = fmax(m, fabs(w2[c * H + hn]));
-    w2m[hn] = m;
-  }
   MlpRsView v;
   v.w1s = w1s;
   v.w2s = w2s;
   v.b1s = b1s;
   v.b2s = b2s;
-  v.w1m = w1m;
-  v.w2m = w2m;
+  v.w1m = b2s + C;
+  v.w2m = v.w1m + F;
   v.F = F;
   v.H = H;
   v.C = C;
+  v.b1max = v.b2max = v.w2sum = 0.0;
+  return v;
+}
+
+__device__ inline void mlp_rs_finish_stage(MlpRsView& v) {
+  const int F = v.F, H = v.H, C = v.C, HP = v.H + 1;
+  double* w1m = const_cast<double*>(v.w1m);
+  double* w2m = const_cast<double*>(v.w2m);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    double m = 0.0;
+    for (int hn = 0; hn < H; ++hn) m = fmax(m, fabs(v.w1s[f * H + hn]));
+    w1m[f] = m;
+  }
+  for (int hn = threadIdx.x; hn < H; hn += blockDim.x) {
+    double m = 0.0;
+    for (int c = 0; c < C; ++c) m = fmax(m, fabs(v.w2s[c * HP + hn]));
+    w2m[hn] = m;
+  }
+  // scalars: every thread derives its own copy from shared memory (broadcast reads)
   double b1max = 0.0, b2max = 0.0, w2sum = 0.0;
   for (int hn = 0; hn < H; ++hn) {
-    b1max = fmax(b1max, fabs(b1[hn]));
+    b1max = fmax(b1max, fabs(v.b1s[hn]));
     double m = 0.0;
-    for (int c = 0; c < C; ++c) m = fmax(m, fabs(w2[c * H + hn]));
+    for (int c = 0; c < C; ++c) m = fmax(m, fabs(v.w2s[c * HP + hn]));
     w2sum += m;  // sum_n max_c |w2_cn|: how far a hidden-layer error can move any logit
   }
-  for (int c = 0; c < C; ++c) b2max = fmax(b2max, fabs(b2[c]));
+  for (int c = 0; c < C; ++c) b2max = fmax(b2max, fabs(v.b2s[c]));
   v.b1max = b1max;
   v.b2max = b2max;
   v.w2sum = w2sum;
-  return v;
 }
 
 struct MlpRowResult {

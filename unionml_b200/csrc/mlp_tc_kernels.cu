@@ -38,7 +38,10 @@
 #include "mlp_rescore.cuh"
 
 #ifndef UML_MLP_QUEUE_DEFAULT
-#define UML_MLP_QUEUE_DEFAULT 1
+// 0: the queue variant lost the same-box A/B (profiles/r02_ab.json: 10M rows 0.640 vs 0.577 ms per step) - the scoring
+// kernel is issue-bound (68 % issue slots), so the 58 000 fp64 rows it takes in slow the pipeline by more than the
+// separate re-score kernel costs.  (The linear tile kernel, with 0.02 % flagged rows, wins with its queue.)
+#define UML_MLP_QUEUE_DEFAULT 0
 #endif
 
 namespace uml {
@@ -143,6 +146,8 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   if constexpr (EXACT && QUEUE) {
     for (int i = threadIdx.x; i < kTcQueueCap + 4; i += blockDim.x) q_slots[i] = 0;
     rs_view = mlp_rs_stage(rs_area, p.w1_64, p.b1_64, p.w2_64, p.b2_64, p.n_in, H, C);
+    __syncthreads();
+    mlp_rs_finish_stage(rs_view);
   }
   double* rs_strips = rs_area + mlp_rs_weight_doubles(p.n_in, H, C);
   if (threadIdx.x == 0) {
