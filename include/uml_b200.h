@@ -195,6 +195,17 @@ UML_API void uml_mlp_free(uml_mlp* m);
 UML_API int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
                     int mode, uml_stats* stats);
 
+/* the MLP predictor from HOST rows through the same chunk pipeline as uml_linear_predict_host_values (pinned bounce
+ * buffers, GPU transpose / down-cast to fp32 - the reference predictor casts features to float32 -, scoring kernel,
+ * fp64 re-score): values_out[i] = the argmax class index of row i as float64, i.e. what
+ * `[float(x) for x in module(features).argmax(1)]` yields (quickstart.py:68-70).  _begin is the asynchronous form
+ * (uml_async_poll / uml_async_finish as for the linear call). */
+UML_API int uml_mlp_predict_host_values(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                                int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, double* values_out,
+                                int mode, int64_t chunk_rows, uml_stats* stats);
+UML_API int uml_mlp_predict_host_values_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows,
+                                      int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                      double* values_out, int mode, int64_t chunk_rows);
 /* fused compute + collective for the MLP predictor: same contract as uml_linear_predict_peers (labels of this rank's
  * rows are stored into every entry of peer_labels at row_offset from the kernel epilogue; int32 or uint8 vectors).
  * Batches whose features are tf32 values (integer / pixel domains) run layer 1 on the tensor cores (tcgen05, stats

@@ -225,6 +225,41 @@ def test_mlp_peer_label_vectors(engine, mlp_golden, monkeypatch):
                 assert (host[:32] == 77).all() and (host[32 + rows :] == 77).all()
 
 
+def test_mlp_host_pipeline_and_async_list(mlp_golden):
+    """mlp_argmax on host frames: the chunk pipeline of the linear predictor (uml_mlp_predict_host_values), and from 1M
+    rows on the asynchronous form that builds the list while the batch is in flight.  Integer frames take the
+    tensor-core kernel, general floats the CUDA-core kernel; both equal the float64 network."""
+    import torch.nn as nn
+
+    from unionml_b200.engine import get_engine
+    from unionml_b200.predictors import device_mlp, mlp_argmax
+
+    w = _weights(mlp_golden)
+    module = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
+    with torch.no_grad():
+        module[0].weight.copy_(torch.from_numpy(w[0])); module[0].bias.copy_(torch.from_numpy(w[1]))
+        module[2].weight.copy_(torch.from_numpy(w[2])); module[2].bias.copy_(torch.from_numpy(w[3]))
+    N = 1_100_001
+    Xi = np.random.default_rng(5).integers(0, 17, size=(64, N)).astype(np.float64)  # feature-major float64 block
+    frame = pd.DataFrame(Xi.T, columns=[f"pixel_{i}" for i in range(64)], copy=False)
+    want = omlp.predict_indices_f64(Xi.T.astype(np.float32), *w).astype(np.float64)
+    got = mlp_argmax(module, frame)  # >= 1M rows: asynchronous list building
+    assert isinstance(got, list) and len(got) == N and isinstance(got[0], float)
+    np.testing.assert_array_equal(np.asarray(got), want)
+    np.testing.assert_array_equal(np.asarray(mlp_argmax(module, frame.iloc[:300_000])), want[:300_000])  # synchronous form
+    eng = get_engine()
+    vals, st = eng.predict_mlp_host_values(device_mlp(module, eng), Xi.T[:500_000], chunk_rows=8192)
+    assert st["path"] == 5
+    np.testing.assert_array_equal(vals, want[:500_000])
+    Xf = np.random.default_rng(6).standard_normal((200_000, 64))  # float64 general values: cast to fp32 like the reference
+    vals, st = eng.predict_mlp_host_values(device_mlp(module, eng), Xf)
+    assert st["path"] == 3
+    np.testing.assert_array_equal(vals, omlp.predict_indices_f64(Xf.astype(np.float32), *w).astype(np.float64))
+    with pytest.raises(ValueError):
+        bad = Xf.copy(); bad[777, 3] = np.inf
+        mlp_argmax(module, bad)
+
+
 def test_generic_shapes_take_the_fp64_kernel(engine):
     rng = np.random.default_rng(0)
     w1, b1 = rng.standard_normal((20, 13)).astype(np.float32), rng.standard_normal(20).astype(np.float32)

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
+#include <sched.h>
 
 #include "uml_common.cuh"
 
@@ -657,6 +658,36 @@ static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, co
   }
 }
 
+// CPUs this process can use: scheduler affinity, capped by the cgroup CPU quota (v2 cpu.max, v1 cfs_quota_us)
+static int usable_cpus() {
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (n <= 0) n = 4;
+  auto read_two = [](const char* path, long long* a, long long* b) -> bool {
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    char first[64] = {0};
+    const int got = fscanf(f, "%63s %lld", first, b);
+    fclose(f);
+    if (got < 1 || strcmp(first, "max") == 0) return false;
+    *a = atoll(first);
+    return got == 2;
+  };
+  long long quota = 0, period = 0;
+  if (read_two("/sys/fs/cgroup/cpu.max", &quota, &period) && quota > 0 && period > 0) {
+    n = std::min<long long>(n, std::max<long long>(1, quota / period));
+  } else {
+    FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+    FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+    if (fq && fp && fscanf(fq, "%lld", &quota) == 1 && fscanf(fp, "%lld", &period) == 1 && quota > 0 && period > 0)
+      n = std::min<long long>(n, std::max<long long>(1, quota / period));
+    if (fq) fclose(fq);
+    if (fp) fclose(fp);
+  }
+  return n;
+}
+
 // pinned bounce buffers (3 slots) + the copy pool, created on first use
 static int ensure_bounce(uml_engine* e, int64_t bytes) {
   if (e->bounce_cap < bytes) {
@@ -671,7 +702,15 @@ static int ensure_bounce(uml_engine* e, int64_t bytes) {
   if (!e->pool) {
     int n = 0;
     if (const char* env = getenv("UML_B200_COPY_THREADS")) n = atoi(env);
-    if (n <= 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, std::thread::hardware_concurrency() / 4u));
+    // default: the CPUs this process may really use (affinity and cgroup quota - the GPU boxes give a container 16 of
+    // 128), minus two so that the caller's own thread (Python turning finished chunks into list pieces in the
+    // asynchronous form) never pushes the group over its quota: CFS then throttles every thread for the rest of the period
+    // ... and the CPUs are shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+    if (n <= 0) {
+      int ranks = 1;
+      if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lw));
+      n = std::min(16, std::max(1, (usable_cpus() - 2) / ranks));
+    }
     e->pool = new CopyPool(n - 1);  // the calling thread is the n-th worker
   }
   return UML_OK;
@@ -1065,6 +1104,29 @@ int uml_labels_push(uml_engine* e, const void* src, void* const* dst, int n_dst,
 // ---------------------------------------------------------------------------------------------------------------
 // host rows -> host labels
 // ---------------------------------------------------------------------------------------------------------------
+// are the first rows of a host source tf32 values once cast to fp32 (low 13 mantissa bits zero)?  A cheap guess used
+// to pick the MLP kernel for the chunk pipeline; correctness never depends on it
+static bool host_sample_is_tf32(const void* host, const SrcLayout& L, int64_t n_rows, int F, int dtype) {
+  const int64_t rows = std::min<int64_t>(n_rows, 2048);
+  const char* base = (const char*)host;
+  for (int64_t r = 0; r < rows; ++r)
+    for (int f = 0; f < F; ++f) {
+      const size_t i = L.feature_major ? (size_t)f * L.pitch_elems + r : (size_t)r * L.pitch_elems + f;
+      float v;
+      switch (dtype) {
+        case UML_F64: v = (float)((const double*)base)[i]; break;
+        case UML_I64: v = (float)((const long long*)base)[i]; break;
+        case UML_I32: v = (float)((const int*)base)[i]; break;
+        case UML_U8: v = (float)((const unsigned char*)base)[i]; break;
+        default: v = ((const float*)base)[i]; break;
+      }
+      uint32_t bits;
+      memcpy(&bits, &v, 4);
+      if (bits & 0x1fffu) return false;
+    }
+  return true;
+}
+
 // B <= kSmallRows: request block -> pinned (device-mapped) buffer -> linear_small_kernel (replayed as a CUDA graph) ->
 // labels written straight into pinned host memory.  fp64 from the caller's own values, so the result is the
 // exact-mode result for either mode.
@@ -1172,14 +1234,21 @@ static int predict_host_small(uml_engine* e, const uml_model* m, const void* hos
 static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
                              int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
                              double* values_out, const double* classes, int n_classes, int mode, int64_t chunk_rows,
-                             uml_stats* stats, std::atomic<int64_t>* progress = nullptr) {
-  if (!e || !m || (!host_ptr && n_rows > 0) || (!labels_out && !values_out && n_rows > 0) || n_rows < 0 || n_features < 1)
+                             uml_stats* stats, std::atomic<int64_t>* progress = nullptr, const uml_mlp* mlp = nullptr) {
+  // exactly one of m (linear classifier) and mlp (2-layer MLP) scores the chunks
+  if (!e || (!m && !mlp) || (!host_ptr && n_rows > 0) || (!labels_out && !values_out && n_rows > 0) || n_rows < 0 ||
+      n_features < 1)
     return UML_ERR_INVALID;
   if (values_out && (!classes || n_classes < 1)) return UML_ERR_INVALID;
   if (mode != UML_PREDICT_FAST && mode != UML_PREDICT_EXACT) UML_FAIL(e, UML_ERR_INVALID, "mode %d", mode);
-  if (n_features != m->n_features_in)
+  if (mlp) {
+    if (n_features != mlp->dm.n_in)
+      UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the module is expecting %d features as input.", n_features,
+               mlp->dm.n_in);
+  } else if (n_features != m->n_features_in) {
     UML_FAIL(e, UML_ERR_SHAPE, "X has %d features, but the estimator is expecting %d features as input.", n_features,
              m->n_features_in);
+  }
   UML_CUDA(e, cudaSetDevice(e->device));
   (void)cudaGetLastError();
   if (stats) memset(stats, 0, sizeof(*stats));
@@ -1188,7 +1257,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   int rc = classify_layout(e, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, &L);
   if (rc != UML_OK) return rc;
   const int F = n_features;
-  if (n_rows <= kSmallRows && (int64_t)F * L.elem * n_rows <= kSmallBytes) {
+  if (!mlp && n_rows <= kSmallRows && (int64_t)F * L.elem * n_rows <= kSmallBytes) {
     rc = predict_host_small(e, m, host_ptr, (int)n_rows, F, L, src_dtype, labels_out, values_out, classes, n_classes, stats);
     if (progress && rc == UML_OK) progress->store(n_rows);
     return rc;
@@ -1267,6 +1336,20 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     if (progress) progress->store(pending[sl].r0 + pending[sl].rows, std::memory_order_release);  // slots flush in row order
     return cudaSuccess;
   };
+
+  // MLP: tensor cores when the features look like tf32 values (a host-side sample of the first rows decides; rows that
+  // are not are caught in the kernel and re-scored, so a wrong guess costs time, never labels), CUDA cores otherwise
+  bool mlp_tc = false, mlp_ffma = false;
+  if (mlp) {
+    std::string why;
+    mlp_tc = uml::mlp_tc_supported(mlp->dm, &why);
+    if (mlp_tc) {
+      const char* env = getenv("UML_B200_MLP_TC");
+      if (env && env[0] == '0') mlp_tc = false;
+      else if (!(env && env[0] == '1')) mlp_tc = host_sample_is_tf32(host_ptr, L, n_rows, F, src_dtype);
+    }
+    mlp_ffma = !mlp_tc && uml::mlp_tma_supported(mlp->dm, &why);
+  }
 
   const bool timed = stats != nullptr;
   cudaStream_t cs = e->stream;
@@ -1371,7 +1454,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     l.ld = ld;
     l.n_rows = rows;
     l.labels = e->d_labels + (int64_t)slot * chunk_rows;
-    if (exact && !direct && lossy_capable(src_dtype)) {
+    if (!mlp && exact && !direct && lossy_capable(src_dtype)) {  // (the reference MLP predictor casts features to float32)
       // flagged rows are re-scored from the caller's own values (the raw chunk is still resident): float64 / int
       // features that do not survive the fp32 down-cast still get sklearn's float64 labels (_base.py:366-396)
       l.src.base = raw;
@@ -1379,7 +1462,39 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
       l.src.row_stride = L.feature_major ? 1 : F;
       l.src.col_stride = L.feature_major ? rows : 1;
     }
-    rc = enqueue_predict(e, m, l, has_map ? &map : nullptr, mode, false, &launches, &path);
+    if (mlp) {
+      uml::MlpTcLaunch out{};
+      out.n_rows = rows;
+      out.labels = l.labels;
+      out.x = xc;
+      out.ld = ld;
+      FlagList fl{e->d_flag_count, e->d_flag_rows, (int)std::min<int64_t>(e->flag_cap, INT32_MAX), e->d_counters};
+      if (mlp_tc && has_map) {
+        bool need_rescore = false;
+        HOST_CUDA(uml::launch_mlp_tc(map, mlp->dm, out, exact, fl, e->info.sm_count, cs, &need_rescore));
+        launches += 1;
+        path = 5;
+        if (need_rescore) {
+          HOST_CUDA(uml::launch_mlp_rescore_f64(mlp->dm, xc, ld, rows, out, fl, false, e->info.sm_count, cs));
+          launches += 1;
+        }
+      } else if (mlp_ffma && has_map) {
+        HOST_CUDA(uml::launch_mlp_tma(map, mlp->dm, xc, rows, out.labels, exact, fl, e->info.sm_count, cs));
+        launches += 1;
+        path = 3;
+        if (exact) {
+          HOST_CUDA(uml::launch_mlp_rescore_f64(mlp->dm, xc, ld, rows, out, fl, false, e->info.sm_count, cs));
+          launches += 1;
+        }
+      } else {
+        HOST_CUDA(uml::launch_mlp_rescore_f64(mlp->dm, xc, ld, rows, out, fl, true, e->info.sm_count, cs));
+        launches += 1;
+        path = 2;
+      }
+      rc = UML_OK;
+    } else {
+      rc = enqueue_predict(e, m, l, has_map ? &map : nullptr, mode, false, &launches, &path);
+    }
     if (rc != UML_OK) {
       cudaStreamSynchronize(cs);
       cudaStreamSynchronize(e->copy_stream);
@@ -1484,6 +1599,40 @@ int uml_linear_predict_host_values_begin(uml_engine* e, const uml_model* m, cons
     e->async_status = predict_host_impl(e, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype,
                                         nullptr, values_out, e->async_classes.data(), n_classes, mode, chunk_rows,
                                         &e->async_stats, &e->async_rows_done);
+    e->async_finished.store(1, std::memory_order_release);
+  });
+  return UML_OK;
+}
+
+// the MLP predictor through the same chunk pipeline: values_out[i] = float(argmax class index of row i), which is what
+// `[float(x) for x in module(features).argmax(1)]` yields (tests/integration/pytorch_app/quickstart.py:68-70)
+int uml_mlp_predict_host_values(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                                int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, double* values_out,
+                                int mode, int64_t chunk_rows, uml_stats* stats) {
+  if (!e || !m || (!values_out && n_rows > 0)) return UML_ERR_INVALID;
+  std::vector<double> classes(m->dm.n_classes);
+  for (int c = 0; c < m->dm.n_classes; ++c) classes[c] = c;
+  return predict_host_impl(e, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, nullptr,
+                           values_out, classes.data(), m->dm.n_classes, mode, chunk_rows, stats, nullptr, m);
+}
+
+int uml_mlp_predict_host_values_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows,
+                                      int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                      double* values_out, int mode, int64_t chunk_rows) {
+  if (!e || !m || (!values_out && n_rows > 0)) return UML_ERR_INVALID;
+  if (!e->async_finished.load() || e->async_thread.joinable())
+    UML_FAIL(e, UML_ERR_INVALID, "an asynchronous call is already in flight on this engine (call uml_async_finish first)");
+  e->async_classes.resize(m->dm.n_classes);
+  for (int c = 0; c < m->dm.n_classes; ++c) e->async_classes[c] = c;
+  e->async_rows_done.store(0);
+  e->async_finished.store(0);
+  e->async_status = UML_OK;
+  memset(&e->async_stats, 0, sizeof(e->async_stats));
+  const int n_classes = m->dm.n_classes;
+  e->async_thread = std::thread([=]() {
+    e->async_status = predict_host_impl(e, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes,
+                                        src_dtype, nullptr, values_out, e->async_classes.data(), n_classes, mode,
+                                        chunk_rows, &e->async_stats, &e->async_rows_done, m);
     e->async_finished.store(1, std::memory_order_release);
   });
   return UML_OK;

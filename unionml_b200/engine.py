@@ -449,7 +449,23 @@ class Engine:
             self._check(st)
         return out, stats.as_dict()
 
-    def predict_host_values_list(self, model: LinearModel, features: Any, classes, exact: bool = True,
+    def predict_mlp_host_values(self, model: MlpModel, features: Any, exact: bool = True,
+                                chunk_rows: int = 0) -> Tuple[np.ndarray, dict]:
+        """Host rows -> argmax class index of the 2-layer MLP per row as float64, through the chunk pipeline
+        (pinned bounce buffers, GPU down-cast to fp32 as the reference predictor does, scoring kernel, fp64 re-score)."""
+        arr = as_feature_array(features)
+        out = np.empty(arr.shape[0], dtype=np.float64)
+        stats = N.Stats()
+        with self._lock:
+            st = N.lib().uml_mlp_predict_host_values(
+                self._h, model._h, C.c_void_p(arr.ctypes.data), arr.shape[0], arr.shape[1], arr.strides[0], arr.strides[1],
+                _DTYPES[arr.dtype], out.ctypes.data_as(C.c_void_p), N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST,
+                chunk_rows, C.byref(stats),
+            )
+            self._check(st)
+        return out, stats.as_dict()
+
+    def predict_host_values_list(self, model, features: Any, classes=None, exact: bool = True,
                                  chunk_rows: int = 0) -> Tuple[list, dict]:
         """``classes_[argmax]`` per row as a Python ``list`` of floats (the predictor contract, ``README.md:87-92``).
 
@@ -459,19 +475,27 @@ class Engine:
         import time
 
         arr = as_feature_array(features)
-        if not (isinstance(classes, np.ndarray) and classes.dtype == np.float64 and classes.flags.c_contiguous):
+        is_mlp = isinstance(model, MlpModel)
+        if not is_mlp and not (isinstance(classes, np.ndarray) and classes.dtype == np.float64 and classes.flags.c_contiguous):
             classes = np.ascontiguousarray(classes, dtype=np.float64)
         n = arr.shape[0]
         values = np.empty(n, dtype=np.float64)
         stats = N.Stats()
         out: list = []
         lib = N.lib()
+        mode = N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST
         with self._lock:
-            st = lib.uml_linear_predict_host_values_begin(
-                self._h, model._h, C.c_void_p(arr.ctypes.data), n, arr.shape[1], arr.strides[0], arr.strides[1],
-                _DTYPES[arr.dtype], classes.ctypes.data_as(C.c_void_p), len(classes), values.ctypes.data_as(C.c_void_p),
-                N.UML_PREDICT_EXACT if exact else N.UML_PREDICT_FAST, chunk_rows,
-            )
+            if is_mlp:  # class index as float, what `[float(x) for x in module(features).argmax(1)]` yields
+                st = lib.uml_mlp_predict_host_values_begin(
+                    self._h, model._h, C.c_void_p(arr.ctypes.data), n, arr.shape[1], arr.strides[0], arr.strides[1],
+                    _DTYPES[arr.dtype], values.ctypes.data_as(C.c_void_p), mode, chunk_rows,
+                )
+            else:
+                st = lib.uml_linear_predict_host_values_begin(
+                    self._h, model._h, C.c_void_p(arr.ctypes.data), n, arr.shape[1], arr.strides[0], arr.strides[1],
+                    _DTYPES[arr.dtype], classes.ctypes.data_as(C.c_void_p), len(classes), values.ctypes.data_as(C.c_void_p),
+                    mode, chunk_rows,
+                )
             self._check(st)
             done, rows_done, finished = 0, C.c_int64(), C.c_int()
             try:

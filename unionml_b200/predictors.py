@@ -305,11 +305,15 @@ def mlp_argmax(module: Any, features: Any) -> List[float]:
     """Drop-in body for the torch quickstart predictor
     ``[float(x) for x in module(process_features(features)).argmax(1)]``: features are cast to float32 exactly as
     ``process_features`` does (``torch.from_numpy(features.values).float()``), the forward pass and argmax run on
-    the GPU, labels come back as Python floats."""
+    the GPU, labels come back as Python floats.  Host frames go through the chunk pipeline of the linear predictor
+    (pinned bounce buffers, GPU down-cast); from 1M rows on the list is built while the batch is still in flight."""
     engine = get_engine()
     dm = device_mlp(module, engine)
     arr = features.to_numpy() if hasattr(features, "to_numpy") else np.asarray(features)
-    batch = engine.stage(arr, keep_f64=False)
-    idx, _ = engine.predict_mlp(dm, batch, exact=_exact_default())
-    batch.free()
-    return idx.astype(np.float64).tolist()
+    _check_min_samples(arr)
+    n_rows = arr.shape[0] if getattr(arr, "ndim", 0) == 2 else 0
+    if n_rows >= _ASYNC_LIST_MIN_ROWS:
+        out, _stats = engine.predict_host_values_list(dm, arr, exact=_exact_default())
+        return out
+    values, _stats = engine.predict_mlp_host_values(dm, arr, exact=_exact_default())
+    return values.tolist()
