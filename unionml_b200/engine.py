@@ -498,11 +498,17 @@ class Engine:
                 )
             self._check(st)
             done, rows_done, finished = 0, C.c_int64(), C.c_int()
+            t0 = time.perf_counter()
+            t_pipeline = t_list = 0.0
             try:
                 while True:
                     lib.uml_async_poll(self._h, C.byref(rows_done), C.byref(finished))
+                    if finished.value and not t_pipeline:
+                        t_pipeline = time.perf_counter() - t0
                     if rows_done.value - done >= 262_144 or (finished.value and rows_done.value > done):
+                        t1 = time.perf_counter()
                         out.extend(values[done : rows_done.value].tolist())
+                        t_list += time.perf_counter() - t1
                         done = rows_done.value
                     elif finished.value:
                         break
@@ -513,7 +519,10 @@ class Engine:
             self._check(st)
         if done < n:  # not reached when the call succeeded (every chunk is flushed before it finishes)
             out.extend(values[done:].tolist())
-        return out, stats.as_dict()
+        d = stats.as_dict()
+        # host-side view of the overlap: when the library thread finished, and how long list building took in total
+        d.update(pipeline_s=t_pipeline, list_s=t_list, total_s=time.perf_counter() - t0)
+        return out, d
 
     def predict_proba(self, model: LinearModel, batch: Batch, out_device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
         """``softmax(X @ coef_.T + intercept_)`` per row (fp32), ``(n_rows, n_classes)``; ``[1 - p, p]`` for a binary model."""
