@@ -169,15 +169,14 @@ UML_API int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, co
                                    int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
                                    const double* classes_host, int n_classes, double* values_out, int mode,
                                    int64_t chunk_rows, uml_stats* stats);
-/* asynchronous form of uml_linear_predict_host_values: _begin returns at once and the pipeline runs on a library thread;
- * uml_async_poll reports how long a prefix of values_out is final (the caller may read it - the Python predictor turns
- * it into list pieces while the rest of the batch is still in flight); uml_async_finish joins and returns the call's
- * status (UML_ERR_NONFINITE ...) and stats.  One asynchronous call per engine; no other call on the engine until
- * _finish.  host_ptr / values_out must stay valid until then. */
-UML_API int uml_linear_predict_host_values_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
-                                         int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes,
-                                         int src_dtype, const double* classes_host, int n_classes, double* values_out,
-                                         int mode, int64_t chunk_rows);
+/* asynchronous form of uml_linear_predict_host: _begin returns at once and the pipeline runs on a library thread;
+ * uml_async_poll reports how long a prefix of labels_out is final (the caller may read it - the Python predictor fills
+ * the List[float] of the predictor contract from it while the rest of the batch is still in flight); uml_async_finish
+ * joins and returns the call's status (UML_ERR_NONFINITE ...) and stats.  One asynchronous call per engine; no other
+ * call on the engine until _finish.  host_ptr / labels_out must stay valid until then. */
+UML_API int uml_linear_predict_host_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
+                                  int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                                  int32_t* labels_out, int mode, int64_t chunk_rows);
 UML_API int uml_async_poll(uml_engine* e, int64_t* rows_done, int* finished);
 UML_API int uml_async_finish(uml_engine* e, uml_stats* stats);
 /* class probabilities of a resident batch: LogisticRegression.predict_proba (sklearn/linear_model/_logistic.py) =
@@ -195,17 +194,16 @@ UML_API void uml_mlp_free(uml_mlp* m);
 UML_API int uml_mlp_predict(uml_engine* e, const uml_mlp* m, const uml_batch* b, int32_t* labels_out, int labels_on_device,
                     int mode, uml_stats* stats);
 
-/* the MLP predictor from HOST rows through the same chunk pipeline as uml_linear_predict_host_values (pinned bounce
- * buffers, GPU transpose / down-cast to fp32 - the reference predictor casts features to float32 -, scoring kernel,
- * fp64 re-score): values_out[i] = the argmax class index of row i as float64, i.e. what
- * `[float(x) for x in module(features).argmax(1)]` yields (quickstart.py:68-70).  _begin is the asynchronous form
- * (uml_async_poll / uml_async_finish as for the linear call). */
-UML_API int uml_mlp_predict_host_values(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
-                                int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, double* values_out,
-                                int mode, int64_t chunk_rows, uml_stats* stats);
-UML_API int uml_mlp_predict_host_values_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows,
-                                      int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
-                                      double* values_out, int mode, int64_t chunk_rows);
+/* the MLP predictor from HOST rows through the same chunk pipeline as uml_linear_predict_host (pinned bounce buffers,
+ * GPU transpose / down-cast to fp32 - the reference predictor casts features to float32 -, scoring kernel, fp64
+ * re-score): labels_out[i] = the argmax class index of row i, what `module(features).argmax(1)` yields
+ * (quickstart.py:68-70).  _begin is the asynchronous form (uml_async_poll / uml_async_finish as for the linear call). */
+UML_API int uml_mlp_predict_host(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                         int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out, int mode,
+                         int64_t chunk_rows, uml_stats* stats);
+UML_API int uml_mlp_predict_host_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                               int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                               int mode, int64_t chunk_rows);
 /* fused compute + collective for the MLP predictor: same contract as uml_linear_predict_peers (labels of this rank's
  * rows are stored into every entry of peer_labels at row_offset from the kernel epilogue; int32 or uint8 vectors).
  * Batches whose features are tf32 values (integer / pixel domains) run layer 1 on the tensor cores (tcgen05, stats

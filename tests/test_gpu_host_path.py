@@ -166,8 +166,9 @@ def test_online_shape_small_batches(engine, digits_model):
 
 
 def test_large_frames_build_the_list_while_the_batch_is_in_flight(engine, digits_model):
-    """>= 1M rows: ``linear_argmax`` runs the pipeline on a library thread (``uml_linear_predict_host_values_begin``)
-    and turns the finished prefix into list pieces meanwhile.  Same labels; NaN still raises; the engine is usable after."""
+    """>= 1M rows: ``linear_argmax`` runs the pipeline on a library thread (``uml_linear_predict_host_begin``) and fills
+    the finished prefix into the list meanwhile (one shared Python float per class, ``csrc_host/uml_pylist.c``).
+    Same labels; NaN still raises; the engine is usable after."""
     from unionml_b200.predictors import linear_argmax
 
     coef, intercept = digits_model["coef"], digits_model["intercept"]
@@ -181,9 +182,11 @@ def test_large_frames_build_the_list_while_the_batch_is_in_flight(engine, digits
         got = linear_argmax(est, frame)
         assert isinstance(got, list) and len(got) == N and isinstance(got[0], float)
         np.testing.assert_array_equal(np.asarray(got), want)
-    out, st = engine.predict_host_values_list(engine.load_linear(coef, intercept), X.T, np.arange(10.0), chunk_rows=8192)
-    np.testing.assert_array_equal(np.asarray(out), want)
-    assert st["n_rows"] == N
+    table = [float(c) * 2.0 for c in range(10)]
+    for asynchronous in (True, False):
+        out, st = engine.predict_host_list(engine.load_linear(coef, intercept), X.T, table, chunk_rows=8192, asynchronous=asynchronous)
+        np.testing.assert_array_equal(np.asarray(out), want * 2.0)
+        assert st["n_rows"] == N and all(type(v) is float for v in out[:100])
     bad = X.T.copy()
     bad[N // 2, 5] = np.nan
     with pytest.raises(ValueError, match="NaN"):

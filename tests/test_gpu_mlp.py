@@ -226,8 +226,8 @@ def test_mlp_peer_label_vectors(engine, mlp_golden, monkeypatch):
 
 
 def test_mlp_host_pipeline_and_async_list(mlp_golden):
-    """mlp_argmax on host frames: the chunk pipeline of the linear predictor (uml_mlp_predict_host_values), and from 1M
-    rows on the asynchronous form that builds the list while the batch is in flight.  Integer frames take the
+    """mlp_argmax on host frames: the chunk pipeline of the linear predictor (uml_mlp_predict_host), and from 1M rows on
+    the asynchronous form that fills the list while the batch is in flight.  Integer frames take the
     tensor-core kernel, general floats the CUDA-core kernel; both equal the float64 network."""
     import torch.nn as nn
 
@@ -248,11 +248,11 @@ def test_mlp_host_pipeline_and_async_list(mlp_golden):
     np.testing.assert_array_equal(np.asarray(got), want)
     np.testing.assert_array_equal(np.asarray(mlp_argmax(module, frame.iloc[:300_000])), want[:300_000])  # synchronous form
     eng = get_engine()
-    vals, st = eng.predict_mlp_host_values(device_mlp(module, eng), Xi.T[:500_000], chunk_rows=8192)
-    assert st["path"] == 5
+    vals, st = eng.predict_mlp_host(device_mlp(module, eng), Xi.T[:500_000], chunk_rows=8192)
+    assert st["path"] == 5 and vals.dtype == np.int32
     np.testing.assert_array_equal(vals, want[:500_000])
     Xf = np.random.default_rng(6).standard_normal((200_000, 64))  # float64 general values: cast to fp32 like the reference
-    vals, st = eng.predict_mlp_host_values(device_mlp(module, eng), Xf)
+    vals, st = eng.predict_mlp_host(device_mlp(module, eng), Xf)
     assert st["path"] == 3
     np.testing.assert_array_equal(vals, omlp.predict_indices_f64(Xf.astype(np.float32), *w).astype(np.float64))
     with pytest.raises(ValueError):

@@ -75,8 +75,30 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_pylist(force)
     return LIB
+
+
+PYLIST_SRC = PKG / "csrc_host" / "uml_pylist.c"
+PYLIST_LIB = LIB_DIR / "libuml_pylist.so"
+
+
+def build_pylist(force: bool = False) -> Path:
+    """The CPython list helper (host glue of the `List[float]` contract; gcc, no CUDA)."""
+    import sysconfig
+
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+    if force or _stale(PYLIST_LIB, [PYLIST_SRC]):
+        cc = shutil.which("gcc") or shutil.which("cc")
+        if cc is None:
+            raise RuntimeError("gcc not found; cannot build libuml_pylist.so")
+        cmd = [cc, "-O2", "-shared", "-fPIC", f"-I{sysconfig.get_paths()['include']}", str(PYLIST_SRC), "-o", str(PYLIST_LIB)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"building {PYLIST_LIB.name} failed:\n{r.stdout}\n{r.stderr}")
+    return PYLIST_LIB
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_pylist(force="--force" in sys.argv))

@@ -89,9 +89,9 @@ SIGNATURES = {
         C.c_int,
         [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int64, C.POINTER(Stats)],
     ),
-    "uml_linear_predict_host_values_begin": (
+    "uml_linear_predict_host_begin": (
         C.c_int,
-        [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int64],
+        [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int64],
     ),
     "uml_async_poll": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "uml_async_finish": (C.c_int, [_P, C.POINTER(Stats)]),
@@ -99,11 +99,11 @@ SIGNATURES = {
     "uml_mlp_load": (C.c_int, [_P, _PP, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "uml_mlp_free": (None, [_P]),
     "uml_mlp_predict": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(Stats)]),
-    "uml_mlp_predict_host_values": (
+    "uml_mlp_predict_host": (
         C.c_int,
         [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int64, C.POINTER(Stats)],
     ),
-    "uml_mlp_predict_host_values_begin": (
+    "uml_mlp_predict_host_begin": (
         C.c_int,
         [_P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int64],
     ),
@@ -111,6 +111,22 @@ SIGNATURES = {
 }
 
 _lib = None
+_pylist = None
+PYLIST_PATH = Path(__file__).resolve().parent / "_lib" / "libuml_pylist.so"
+
+
+def pylist():
+    """The CPython list helper (``csrc_host/uml_pylist.c``), loaded with ``PyDLL`` so the GIL stays held; ``None`` when
+    it has not been built (callers then fall back to ``ndarray.tolist()``)."""
+    global _pylist
+    if _pylist is None:
+        if not PYLIST_PATH.exists():
+            return None
+        h = C.PyDLL(str(PYLIST_PATH))
+        h.uml_list_fill_from_labels.restype = C.c_int
+        h.uml_list_fill_from_labels.argtypes = [C.py_object, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.py_object]
+        _pylist = h
+    return _pylist
 
 
 class NativeLibraryMissing(ImportError):

@@ -186,7 +186,7 @@ struct uml_engine {
   std::atomic<int> async_finished{1};
   int async_status = UML_OK;
   uml_stats async_stats{};
-  std::vector<double> async_classes;
+
   bool small_graph_ok = true;
   HostMirror* h = nullptr;
 };
@@ -1580,62 +1580,51 @@ int uml_linear_predict_host_values(uml_engine* e, const uml_model* m, const void
 }
 
 // asynchronous variant: the whole pipeline runs on a library thread so that the caller (Python building the
-// List[float] of the predictor contract, ~15 ns per element) can consume values_out[0, rows_done) while the rest of the
-// batch is still crossing PCIe.  One call in flight per engine; no other call on the engine until _finish.
-int uml_linear_predict_host_values_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows,
-                                         int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
-                                         const double* classes_host, int n_classes, double* values_out, int mode,
-                                         int64_t chunk_rows) {
-  if (!e || !m || (!values_out && n_rows > 0) || !classes_host || n_classes < 1) return UML_ERR_INVALID;
+// List[float] of the predictor contract) can consume labels_out[0, rows_done) while the rest of the batch is still
+// crossing PCIe.  One call in flight per engine; no other call on the engine until _finish.
+static int async_begin(uml_engine* e, const uml_model* m, const uml_mlp* mlp, const void* host_ptr, int64_t n_rows,
+                       int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
+                       int32_t* labels_out, int mode, int64_t chunk_rows) {
+  if (!e || (!m && !mlp) || (!labels_out && n_rows > 0)) return UML_ERR_INVALID;
   if (!e->async_finished.load() || e->async_thread.joinable())
     UML_FAIL(e, UML_ERR_INVALID, "an asynchronous call is already in flight on this engine (call uml_async_finish first)");
-  if (n_classes < m->dm.n_classes) UML_FAIL(e, UML_ERR_INVALID, "classes_ has %d entries, the model scores %d classes", n_classes, m->dm.n_classes);
-  e->async_classes.assign(classes_host, classes_host + n_classes);
   e->async_rows_done.store(0);
   e->async_finished.store(0);
   e->async_status = UML_OK;
   memset(&e->async_stats, 0, sizeof(e->async_stats));
   e->async_thread = std::thread([=]() {
     e->async_status = predict_host_impl(e, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype,
-                                        nullptr, values_out, e->async_classes.data(), n_classes, mode, chunk_rows,
-                                        &e->async_stats, &e->async_rows_done);
+                                        labels_out, nullptr, nullptr, 0, mode, chunk_rows, &e->async_stats,
+                                        &e->async_rows_done, mlp);
     e->async_finished.store(1, std::memory_order_release);
   });
   return UML_OK;
 }
 
-// the MLP predictor through the same chunk pipeline: values_out[i] = float(argmax class index of row i), which is what
-// `[float(x) for x in module(features).argmax(1)]` yields (tests/integration/pytorch_app/quickstart.py:68-70)
-int uml_mlp_predict_host_values(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
-                                int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, double* values_out,
-                                int mode, int64_t chunk_rows, uml_stats* stats) {
-  if (!e || !m || (!values_out && n_rows > 0)) return UML_ERR_INVALID;
-  std::vector<double> classes(m->dm.n_classes);
-  for (int c = 0; c < m->dm.n_classes; ++c) classes[c] = c;
-  return predict_host_impl(e, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, nullptr,
-                           values_out, classes.data(), m->dm.n_classes, mode, chunk_rows, stats, nullptr, m);
+int uml_linear_predict_host_begin(uml_engine* e, const uml_model* m, const void* host_ptr, int64_t n_rows, int n_features,
+                                  int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                                  int mode, int64_t chunk_rows) {
+  if (!m) return UML_ERR_INVALID;
+  return async_begin(e, m, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, labels_out,
+                     mode, chunk_rows);
 }
 
-int uml_mlp_predict_host_values_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows,
-                                      int n_features, int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype,
-                                      double* values_out, int mode, int64_t chunk_rows) {
-  if (!e || !m || (!values_out && n_rows > 0)) return UML_ERR_INVALID;
-  if (!e->async_finished.load() || e->async_thread.joinable())
-    UML_FAIL(e, UML_ERR_INVALID, "an asynchronous call is already in flight on this engine (call uml_async_finish first)");
-  e->async_classes.resize(m->dm.n_classes);
-  for (int c = 0; c < m->dm.n_classes; ++c) e->async_classes[c] = c;
-  e->async_rows_done.store(0);
-  e->async_finished.store(0);
-  e->async_status = UML_OK;
-  memset(&e->async_stats, 0, sizeof(e->async_stats));
-  const int n_classes = m->dm.n_classes;
-  e->async_thread = std::thread([=]() {
-    e->async_status = predict_host_impl(e, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes,
-                                        src_dtype, nullptr, values_out, e->async_classes.data(), n_classes, mode,
-                                        chunk_rows, &e->async_stats, &e->async_rows_done, m);
-    e->async_finished.store(1, std::memory_order_release);
-  });
-  return UML_OK;
+// the MLP predictor through the same chunk pipeline: labels_out[i] = argmax class index of row i, i.e. what
+// `module(features).argmax(1)` yields (tests/integration/pytorch_app/quickstart.py:68-70)
+int uml_mlp_predict_host(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                         int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out, int mode,
+                         int64_t chunk_rows, uml_stats* stats) {
+  if (!e || !m || (!labels_out && n_rows > 0)) return UML_ERR_INVALID;
+  return predict_host_impl(e, nullptr, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype,
+                           labels_out, nullptr, nullptr, 0, mode, chunk_rows, stats, nullptr, m);
+}
+
+int uml_mlp_predict_host_begin(uml_engine* e, const uml_mlp* m, const void* host_ptr, int64_t n_rows, int n_features,
+                               int64_t row_stride_bytes, int64_t col_stride_bytes, int src_dtype, int32_t* labels_out,
+                               int mode, int64_t chunk_rows) {
+  if (!m) return UML_ERR_INVALID;
+  return async_begin(e, nullptr, m, host_ptr, n_rows, n_features, row_stride_bytes, col_stride_bytes, src_dtype, labels_out,
+                     mode, chunk_rows);
 }
 
 int uml_async_poll(uml_engine* e, int64_t* rows_done, int* finished) {

@@ -234,16 +234,18 @@ def linear_accuracy(estimator: Any, features: Any, target: Any, exact: bool | No
 def linear_argmax(estimator: Any, features: Any) -> List[float]:
     """Drop-in body for ``@model.predictor``: class labels as Python floats.
 
-    Numeric ``classes_`` (the canonical case): ``classes_.take`` and the float conversion run on the device
-    (``uml_linear_predict_host_values``) and the float64 vector becomes the list in one ``tolist()``."""
+    Numeric ``classes_`` (the canonical case): int32 labels come back from the chunk pipeline and the list references
+    one Python float per class (``Engine.predict_host_list``; from 1M rows on it is filled while the batch is still in
+    flight); requests of up to 64 rows take the zero-copy online kernel and ``tolist()``."""
     engine = get_engine()
     dm = device_model(estimator, engine)
     if dm.classes_f64 is not None:
         _check_feature_names(estimator, features)
         _check_min_samples(features)
         n_rows = getattr(features, "shape", (0,))[0]
-        if n_rows >= _ASYNC_LIST_MIN_ROWS:
-            out, stats = engine.predict_host_values_list(dm, features, dm.classes_f64, exact=_exact_default())
+        if n_rows > _SMALL_ROWS:
+            # labels come back as int32; the list references one Python float per class (engine.predict_host_list)
+            out, stats = engine.predict_host_list(dm, features, dm.class_table, exact=_exact_default())
             _note_ambiguous(stats)
             return out
         values, stats = engine.predict_host_values(dm, features, dm.classes_f64, exact=_exact_default())
@@ -252,8 +254,8 @@ def linear_argmax(estimator: Any, features: Any) -> List[float]:
     return [float(x) for x in linear_predict_labels(estimator, features)]
 
 
-#: from this many rows on, the list of the predictor contract is built piecewise while the batch is still in flight
-_ASYNC_LIST_MIN_ROWS = 1_000_000
+#: the online shape (one zero-copy kernel, values straight back); larger batches take the label + list-fill route
+_SMALL_ROWS = 64
 
 
 def linear_predict_proba(estimator: Any, features: Any) -> np.ndarray:
@@ -306,14 +308,10 @@ def mlp_argmax(module: Any, features: Any) -> List[float]:
     ``[float(x) for x in module(process_features(features)).argmax(1)]``: features are cast to float32 exactly as
     ``process_features`` does (``torch.from_numpy(features.values).float()``), the forward pass and argmax run on
     the GPU, labels come back as Python floats.  Host frames go through the chunk pipeline of the linear predictor
-    (pinned bounce buffers, GPU down-cast); from 1M rows on the list is built while the batch is still in flight."""
+    (pinned bounce buffers, GPU down-cast); from 1M rows on the list is filled while the batch is still in flight."""
     engine = get_engine()
     dm = device_mlp(module, engine)
     arr = features.to_numpy() if hasattr(features, "to_numpy") else np.asarray(features)
     _check_min_samples(arr)
-    n_rows = arr.shape[0] if getattr(arr, "ndim", 0) == 2 else 0
-    if n_rows >= _ASYNC_LIST_MIN_ROWS:
-        out, _stats = engine.predict_host_values_list(dm, arr, exact=_exact_default())
-        return out
-    values, _stats = engine.predict_mlp_host_values(dm, arr, exact=_exact_default())
-    return values.tolist()
+    out, _stats = engine.predict_host_list(dm, arr, dm.class_table, exact=_exact_default())
+    return out
