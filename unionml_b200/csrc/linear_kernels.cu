@@ -187,7 +187,8 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + CP);
   uint64_t* empty_bar = full_bar + S;
   // QUEUE kernels: rows flagged by the scoring warps travel through this shared-memory queue to the re-score warp
-  // (slot value = row + 1, 0 = empty); ctl[0] = tail (reserved), ctl[1] = head (consumed), ctl[2] = scoring warps done
+  // (slot value = row + 1, 0 = empty); ctl[0] = tail (reserved), ctl[1] = head (tickets claimed), ctl[2] = scoring
+  // warps done, ctl[3] = slots consumed
   int* q_slots = reinterpret_cast<int*>(empty_bar + S);
   int* q_ctl = q_slots + kQueueCap;
 
@@ -423,8 +424,8 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             int base = -1;
             if (lane == 0) {
               const int tail = *reinterpret_cast<volatile int*>(&q_ctl[0]);
-              const int head = *reinterpret_cast<volatile int*>(&q_ctl[1]);
-              if (tail - head <= kQueueCap - kQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
+              const int consumed = *reinterpret_cast<volatile int*>(&q_ctl[3]);
+              if (tail - consumed <= kQueueCap - kQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= 0) {
@@ -433,7 +434,10 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
               for (int j = 0; j < R; ++j) {
                 if (flag[j]) {
                   const int slot = (off + __popc(masks[j] & ((1u << lane) - 1u))) & (kQueueCap - 1);
-                  *reinterpret_cast<volatile int*>(&q_slots[slot]) = static_cast<int>(row0 + lane + 32 * j) + 1;
+                  volatile int* sp = reinterpret_cast<volatile int*>(&q_slots[slot]);
+                  while (*sp != 0) {  // only if a consumer claimed this slot's previous ticket and has not read it yet
+                  }
+                  *sp = static_cast<int>(row0 + lane + 32 * j) + 1;
                 }
                 off += __popc(masks[j]);
               }
@@ -466,45 +470,42 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
           atomicAdd(&q_ctl[2], 1);  // this scoring warp has published everything it will ever publish
         }
       }
-    }
-    if constexpr (EXACT && QUEUE) {
-      if (warp == kConsumerWarps + 1) {
-        // ===================== fp64 re-score warp: drains the queue while the scoring warps stream =====================
+      // ===================== fp64 re-score: warp 9 drains the queue while the scoring warps stream; a scoring warp
+      // that has finished its tiles joins in, so a long tail of flagged rows (wide rows, many near-ties) is shared
+      // by all ten warps instead of waiting for one =====================
+      int n_done = 0;
+      for (;;) {
+        // claim the next ticket, then wait until its slot is published (lane 0 polls and broadcasts: the lanes of a
+        // warp need not run in lockstep)
         int t = 0;
+        if (lane == 0) t = atomicAdd(&q_ctl[1], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        int v = 0;
         for (;;) {
-          // lane 0 looks at the queue and broadcasts what it saw: the lanes of a warp need not run in lockstep, so
-          // thirty-two separate volatile reads could disagree about a slot that is being published
-          int v = 0, state = 0;  // state: 1 = done, nothing left; 2 = idle, poll again after a short sleep
+          int state = 0;  // 1: nothing will ever be published for this ticket
           if (lane == 0) {
             v = *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]);
-            if (v == 0) {
-              if (*reinterpret_cast<volatile int*>(&q_ctl[2]) == kConsumerWarps) {
-                __threadfence_block();
-                state = (t == *reinterpret_cast<volatile int*>(&q_ctl[0])) ? 1 : 0;  // 0: published, read the slot again
-              } else {
-                state = 2;
-              }
+            if (v == 0 && *reinterpret_cast<volatile int*>(&q_ctl[2]) == kConsumerWarps) {
+              __threadfence_block();
+              if (t >= *reinterpret_cast<volatile int*>(&q_ctl[0])) state = 1;
             }
           }
           v = __shfl_sync(0xffffffffu, v, 0);
           state = __shfl_sync(0xffffffffu, state, 0);
-          if (v == 0) {
-            if (state == 1) break;
-            if (state == 2) __nanosleep(200);
-            continue;
-          }
-          __syncwarp();
-          if (lane == 0) {
-            *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]) = 0;
-            *reinterpret_cast<volatile int*>(&q_ctl[1]) = t + 1;
-          }
-          ++t;
-          const long long row = static_cast<long long>(v) - 1;
-          const int idx64 = rescore_row_inline(p, row, lane);
-          if (lane == 0) store_final_label(p, row, idx64);
+          if (v != 0 || state == 1) break;
+          __nanosleep(200);
         }
-        if (lane == 0 && t > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(t));
+        if (v == 0) break;
+        if (lane == 0) {
+          *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]) = 0;
+          atomicAdd(&q_ctl[3], 1);
+        }
+        const long long row = static_cast<long long>(v) - 1;
+        const int idx64 = rescore_row_inline(p, row, lane);
+        if (lane == 0) store_final_label(p, row, idx64);
+        ++n_done;
       }
+      if (lane == 0 && n_done > 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n_done));
     }
   }
 }
