@@ -532,10 +532,24 @@ struct RescoreParams {
   int wire_u8;
   long long row_offset;
   unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] flagged (re-scored) rows
+  int smem_weights;              // W, b staged in dynamic shared memory ((C F + C) doubles)
 };
 
 
 __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
+  // W (fp64, [C][F]) and b are staged in shared memory when they fit (p.smem_weights): a wide model (784 x 10 = 62 KB)
+  // would otherwise be re-read from L2 for every re-scored row - 8 600 rows x 62 KB = 0.5 GB per cfg-3 step
+  extern __shared__ double rs_w[];
+  const double* w64 = p.w64;
+  const double* b64 = p.b64;
+  if (p.smem_weights) {
+    const int nw = p.n_classes * p.n_features;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) rs_w[i] = p.w64[i];
+    for (int i = threadIdx.x; i < p.n_classes; i += blockDim.x) rs_w[nw + i] = p.b64[i];
+    w64 = rs_w;
+    b64 = rs_w + nw;
+    __syncthreads();
+  }
   pdl_wait_for_predecessor();  // the flag list is written by the scoring kernel this launch depends on
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -549,13 +563,13 @@ __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p)
     RowScore r;
     if (p.src.base) {
       const SrcView v = p.src;
-      r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, F, C, lane);
+      r = score_row_f64([&](int f) { return load_src(v, row, f); }, w64, b64, F, C, lane);
     } else if (p.x64) {
       const double* xr64 = p.x64 + row * p.ld64;
-      r = score_row_f64([&](int f) { return xr64[f]; }, p.w64, p.b64, F, C, lane);
+      r = score_row_f64([&](int f) { return xr64[f]; }, w64, b64, F, C, lane);
     } else {
       const float* xr = p.x + row * p.ld;
-      r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, p.w64, p.b64, F, C, lane);
+      r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, w64, b64, F, C, lane);
     }
     if (lane == 0) {
       if (p.labels) p.labels[row] = r.idx;
@@ -792,7 +806,10 @@ bool linear_queue_rescore() {
 cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& m, const LinearLaunch& l, bool exact,
                               const FlagList& flags, int sm_count, cudaStream_t stream, std::string* err,
                               bool* rescore_kernel_needed) {
-  const bool inline_rescore = exact && linear_queue_rescore();
+  // the in-kernel queue re-scores rows with W in global memory / L2: fine for a 5 KB model, not for 62 KB of fp64
+  // weights per row (cfg 3) - wide models take the re-score kernel, which stages W in shared memory
+  const bool small_model = static_cast<size_t>(m.n_classes) * m.n_features * sizeof(double) <= 16 * 1024;
+  const bool inline_rescore = exact && small_model && linear_queue_rescore();
   if (rescore_kernel_needed) *rescore_kernel_needed = exact && !inline_rescore;
   if (!linear_tma_supported(m, err)) return cudaErrorInvalidValue;
   if (l.n_rows <= 0) return cudaSuccess;
@@ -862,13 +879,23 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   for (int i = 0; i < 8; ++i) p.peers[i] = i < l.n_peers ? l.peers[i] : nullptr;
   p.row_offset = l.row_offset;
   p.counters = flags.counters;
-  // flagged rows are few (0.02 % on cfg 2): a grid of 2 blocks per SM starts and drains faster than 8; the all-rows
+  // shared-memory copy of W, b when it fits next to nothing else (<= 200 KB)
+  size_t smem = (static_cast<size_t>(m.n_classes) * m.n_features + m.n_classes) * sizeof(double);
+  if (smem > 200 * 1024) smem = 0;
+  p.smem_weights = smem > 0 ? 1 : 0;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(rescore_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  // flagged rows are few (0.02 % on cfg 2): a grid of <= 2 blocks per SM starts and drains faster than 8; the all-rows
   // path (generic shapes) wants every resident warp
-  static int per_sm = 0;
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_f64_kernel, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_f64_kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long blocks = static_cast<long long>(sm_count) * (all_rows ? per_sm : std::min(per_sm, 2));
   if (all_rows) blocks = std::min<long long>(blocks, (l.n_rows + 7) / 8);
-  return launch_dependent(rescore_f64_kernel, static_cast<int>(std::max<long long>(1, blocks)), 256, 0, stream, p);
+  return launch_dependent(rescore_f64_kernel, static_cast<int>(std::max<long long>(1, blocks)), 256, smem, stream, p);
 }
 
 }  // namespace uml
