@@ -36,7 +36,6 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 UNIT = "rows/s"
 CONFIGS = {
@@ -485,6 +484,39 @@ def run_gpu_arm(args, cfg):
         chosen = min(gather_ab, key=gather_ab.get)
     step, labels_all = make_step(chosen)
     ex = candidates.get(chosen) if world > 1 else None
+    # N > 1: a step is 2-4 launches of 60-200 us in total, issued from Python on every rank; capture it once in a CUDA
+    # graph and replay it, so the timed loop measures the GPUs and not the launch rate of the host.  Falls back to
+    # eager launches when the capture is refused (reported in the JSON line).
+    graph_note = "eager launches"
+    if world > 1 and not args.no_graph:
+        eager_step = step
+        try:
+            for _ in range(3):
+                eager_step()
+            barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                eager_step()
+            barrier()
+            g.replay()
+            barrier()
+            step = g.replay
+            graph_note = "one CUDA graph per step (captured once, replayed)"
+        except Exception as exc:  # capture refused: keep launching eagerly
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            torch.cuda.set_stream(stream)
+            eng.set_stream(stream.cuda_stream)
+            step = eager_step
+            graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
+        # every rank must take the same route
+        flag = torch.tensor([1 if step is not eager_step else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and step is not eager_step:
+            step = eager_step
+            graph_note = "eager launches (a peer rank could not capture)"
     how = "one NVLS multicast store per tile" if (ex is not None and ex.multicast) else "one store per peer per tile"
     args.gather_used = {
         "fused": f"fused uint8 label stores ({how}) from the kernel epilogue over NVLink (symmetric memory) + barrier",
@@ -641,7 +673,8 @@ def run_gpu_arm(args, cfg):
             "scaling": args.scaling_resolved, "vs_baseline": None, "dtype": "f32" if kind == "linear" else "tf32x2+f32",
             "data": "synthetic", "config": workload_config(args, cfg, world), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
-            "gather_ab_ms_per_step": gather_ab or None, "device": eng.info,
+            "gather_ab_ms_per_step": gather_ab or None, "step_launch": graph_note if world > 1 else "eager launches",
+            "device": eng.info,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -790,6 +823,7 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "fused", "push", "push4", "nccl"],
                     help="label exchange for --gpus > 1 (auto: short in-process A/B, fastest wins, all reported)")
     ap.add_argument("--no-multicast", action="store_true", help="per-peer stores instead of the NVLS multicast alias")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from a committed ncu capture")
     args = ap.parse_args()
     args.scaling_resolved = "strong" if args.scaling in ("auto", "strong") else "weak"
