@@ -21,4 +21,20 @@ eng.predict_host(m, X, exact=True, chunk_rows=4096)
 buf = eng.device_alloc(b.n_rows)
 eng.predict_peers(m, b, [buf.ptr], 0, exact=True, want_stats=True, label_bytes=1)
 eng.take_labels(buf.ptr, b.n_rows, np.arange(10.0), label_bytes=1)
+# round 2: tensor-core MLP kernel (+ peer stores, queue re-score variant), CUDA-core MLP kernel on float rows, re-score from
+# the caller's float64 values, online small-batch kernel, predict_proba, MLP host pipeline, asynchronous host call
+import os as _os
+
+eng.predict_mlp_peers(mlp, b, [buf.ptr], 0, exact=True, want_stats=True, label_bytes=1)
+Xf = np.random.default_rng(1).standard_normal((20_001, 64))
+bf = eng.stage(Xf)
+eng.predict_mlp(mlp, bf, exact=True)                     # general floats: FFMA kernel
+eng.predict_host(m, Xf, exact=True, chunk_rows=4096)     # float64 source: re-score reads the raw chunk
+eng.predict_host(m, np.asfortranarray(Xf[:32]), exact=True)   # online shape: zero-copy kernel, graph replay
+eng.predict_host(m, np.asfortranarray(Xf[:32]), exact=True)
+eng.predict_proba(m, b)
+eng.predict_mlp_host(mlp, X.astype(np.float64), chunk_rows=4096)
+eng.predict_host_list(m, X.astype(np.float64), [float(c) for c in range(10)], chunk_rows=4096, asynchronous=True)
+m0 = eng.load_linear(np.zeros((5, 64)), np.zeros(5))    # every row a tie: the queue backs up, scoring warps re-score their own rows
+eng.predict(m0, b, exact=True)
 print("sanitizer driver ok")
