@@ -423,8 +423,8 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             __threadfence();  // the provisional labels are visible before the re-score warp may overwrite them
             int base = -1;
             if (lane == 0) {
-              const int tail = *reinterpret_cast<volatile int*>(&q_ctl[0]);
-              const int consumed = *reinterpret_cast<volatile int*>(&q_ctl[3]);
+              const int tail = atomicAdd(&q_ctl[0], 0);
+              const int consumed = atomicAdd(&q_ctl[3], 0);
               if (tail - consumed <= kQueueCap - kQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -434,10 +434,11 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
               for (int j = 0; j < R; ++j) {
                 if (flag[j]) {
                   const int slot = (off + __popc(masks[j] & ((1u << lane) - 1u))) & (kQueueCap - 1);
-                  volatile int* sp = reinterpret_cast<volatile int*>(&q_slots[slot]);
-                  while (*sp != 0) {  // only if a consumer claimed this slot's previous ticket and has not read it yet
+                  // (atomics, not plain volatile accesses: the queue is a lock-free hand-off between warps and the
+                  // race checker should see it as one)
+                  while (atomicAdd(&q_slots[slot], 0) != 0) {  // only if the slot's previous ticket is claimed but not read yet
                   }
-                  *sp = static_cast<int>(row0 + lane + 32 * j) + 1;
+                  atomicExch(&q_slots[slot], static_cast<int>(row0 + lane + 32 * j) + 1);
                 }
                 off += __popc(masks[j]);
               }
@@ -484,10 +485,10 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
         for (;;) {
           int state = 0;  // 1: nothing will ever be published for this ticket
           if (lane == 0) {
-            v = *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]);
-            if (v == 0 && *reinterpret_cast<volatile int*>(&q_ctl[2]) == kConsumerWarps) {
+            v = atomicAdd(&q_slots[t & (kQueueCap - 1)], 0);
+            if (v == 0 && atomicAdd(&q_ctl[2], 0) == kConsumerWarps) {
               __threadfence_block();
-              if (t >= *reinterpret_cast<volatile int*>(&q_ctl[0])) state = 1;
+              if (t >= atomicAdd(&q_ctl[0], 0)) state = 1;
             }
           }
           v = __shfl_sync(0xffffffffu, v, 0);
@@ -497,7 +498,7 @@ linear_argmax_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
         }
         if (v == 0) break;
         if (lane == 0) {
-          *reinterpret_cast<volatile int*>(&q_slots[t & (kQueueCap - 1)]) = 0;
+          atomicExch(&q_slots[t & (kQueueCap - 1)], 0);
           atomicAdd(&q_ctl[3], 1);
         }
         const long long row = static_cast<long long>(v) - 1;

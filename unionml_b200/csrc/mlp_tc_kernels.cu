@@ -159,7 +159,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       mbar_init(&dfull_bar[a], 1);
       mbar_init(&dempty_bar[a], 4);  // the four epilogue warps
     }
-    for (int s = 0; s < kTcSlots; ++s) mbar_init(&a1_bar[s], 4);
+    for (int s = 0; s < kTcSlots; ++s) mbar_init(&a1_bar[s], kTileRows);  // every scan thread arrives for its own row
     fence_barrier_init();
   }
   if (warp == kTcMmaWarp) tmem_alloc<TMEM_COLS>(tmem_base_s);
@@ -259,8 +259,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       // a row whose features are not tf32 values was scored from truncated inputs: A1 = +inf sends it to the fp64 re-score
       const uint32_t slot = it % kTcSlots;
       a1_s[slot * kTileRows + row] = (lowbits & 0x1fffu) ? INFINITY : (a1 + p.b1max);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a1_bar[slot]);
+      mbar_arrive(&a1_bar[slot]);  // release: this thread's A1 is visible to whoever completes the wait
     }
   } else if (warp < 4 + kTcEpilogueWarps) {
     // ===================== epilogue warps 4..11: TMEM lane = row; set 0 (warps 4-7) even tiles, set 1 odd tiles ====
@@ -354,18 +353,17 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
             const int total = __popc(mask);
             int base = -1;
             if (lane == 0) {
-              const int tail = *reinterpret_cast<volatile int*>(&q_ctl[0]);
-              const int consumed = *reinterpret_cast<volatile int*>(&q_ctl[3]);
+              const int tail = atomicAdd(&q_ctl[0], 0);
+              const int consumed = atomicAdd(&q_ctl[3], 0);
               if (tail - consumed <= kTcQueueCap - kTcQueueHeadroom) base = atomicAdd(&q_ctl[0], total);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= 0) {
               if (flagged) {
                 const int slot = (base + __popc(mask & ((1u << lane) - 1u))) & (kTcQueueCap - 1);
-                volatile int* sp = reinterpret_cast<volatile int*>(&q_slots[slot]);
-                while (*sp != 0) {  // only if a consumer claimed this slot's previous ticket and has not read it yet
+                while (atomicAdd(&q_slots[slot], 0) != 0) {  // only if the slot's previous ticket is claimed but not read yet
                 }
-                *sp = static_cast<int>(row) + 1;
+                atomicExch(&q_slots[slot], static_cast<int>(row) + 1);
               }
             } else {
               // queue backed up (most rows near-ties): this warp re-scores its own rows in fp64
@@ -418,10 +416,10 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         for (;;) {
           int state = 0;  // 1: nothing will ever be published for this ticket
           if (lane == 0) {
-            v = *reinterpret_cast<volatile int*>(&q_slots[t & (kTcQueueCap - 1)]);
-            if (v == 0 && *reinterpret_cast<volatile int*>(&q_ctl[2]) == kTcEpilogueWarps) {
+            v = atomicAdd(&q_slots[t & (kTcQueueCap - 1)], 0);
+            if (v == 0 && atomicAdd(&q_ctl[2], 0) == kTcEpilogueWarps) {
               __threadfence_block();
-              if (t >= *reinterpret_cast<volatile int*>(&q_ctl[0])) state = 1;
+              if (t >= atomicAdd(&q_ctl[0], 0)) state = 1;
             }
           }
           v = __shfl_sync(0xffffffffu, v, 0);
@@ -431,7 +429,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         }
         if (v == 0) break;
         if (lane == 0) {
-          *reinterpret_cast<volatile int*>(&q_slots[t & (kTcQueueCap - 1)]) = 0;
+          atomicExch(&q_slots[t & (kTcQueueCap - 1)], 0);
           atomicAdd(&q_ctl[3], 1);
         }
         const long long frow = static_cast<long long>(v) - 1;
