@@ -113,6 +113,47 @@ def test_lossy_integer_features_and_fp32_overflow(engine):
     assert st["n_nonfinite"] == 0
 
 
+def test_lossless_float64_frames_cross_the_link_as_fp32(engine, monkeypatch):
+    """Integer-valued float64 frames (the digits / pixel domain) are narrowed to fp32 by the gather threads, every value
+    checked; the first chunk with a value that does not survive the down-cast - and all chunks after it - travel as
+    float64 and keep the float64 re-score from the caller's values.  Labels are the float64 labels either way."""
+    rng = np.random.default_rng(21)
+    coef, intercept = rng.standard_normal((5, 12)), rng.standard_normal(5)
+    m = engine.load_linear(coef, intercept)
+    N, chunk = 300_000, 65_536
+    Xi = rng.integers(0, 17, size=(N, 12)).astype(np.float64)
+    want = olin.predict_indices(olin.decision_function(Xi, coef, intercept)).astype(np.int32)
+    for name, arr in {"c_order": Xi, "f_order": np.asfortranarray(Xi)}.items():
+        idx, st = engine.predict_host(m, arr, exact=True, chunk_rows=chunk)
+        np.testing.assert_array_equal(idx, want, err_msg=name)
+        assert st["h2d_bytes"] == N * 12 * 4, name  # half the float64 bytes
+    monkeypatch.setenv("UML_B200_NO_NARROW", "1")
+    idx, st = engine.predict_host(m, np.asfortranarray(Xi), exact=True, chunk_rows=chunk)
+    np.testing.assert_array_equal(idx, want)
+    assert st["h2d_bytes"] == N * 12 * 8
+    monkeypatch.delenv("UML_B200_NO_NARROW")
+    # a strided row-major source (column slice of a wider array) is gathered row by row: not narrowed
+    idx, st = engine.predict_host(m, np.hstack([Xi, Xi])[:, :12], exact=True, chunk_rows=chunk)
+    np.testing.assert_array_equal(idx, want)
+    assert st["h2d_bytes"] == N * 12 * 8
+    # chunks 0-1 lossless, planted +-1e-9 near-ties from row 150 000 on: chunk 2 is detected lossy on the host, is sent
+    # again as float64, and the rest of the call stays float64
+    Xm = Xi.copy()
+    Xm[150_000:] = planted_near_ties(rng, coef, intercept, N - 150_000)
+    want = olin.predict_indices(olin.decision_function(Xm, coef, intercept)).astype(np.int32)
+    rounded = olin.predict_indices(olin.decision_function(Xm.astype(np.float32).astype(np.float64), coef, intercept))
+    assert (rounded != want).sum() > 1000
+    for name, arr in {"c_order": Xm, "f_order": np.asfortranarray(Xm)}.items():
+        idx, st = engine.predict_host(m, arr, exact=True, chunk_rows=chunk)
+        np.testing.assert_array_equal(idx, want, err_msg=name)
+        assert st["h2d_bytes"] == 2 * chunk * 12 * 4 + (N - 2 * chunk) * 12 * 8, name
+    # a NaN is "not lossless" for the gather threads: the chunk travels as float64 and the staging kernel reports it
+    Xn = Xi.copy()
+    Xn[77, 3] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        engine.predict_host(m, np.asfortranarray(Xn), exact=True, chunk_rows=chunk)
+
+
 def test_mnist_scaled_float64_frame_one_million(engine):
     """cfg 3's real-world shape: pixels / 255 as float64 (not fp32-representable), 784 features, through linear_argmax."""
     from unionml_b200.predictors import linear_argmax

@@ -67,6 +67,9 @@ class CopyPool {
     const char* src;
     size_t n;
     size_t rows = 1, dpitch = 0, spitch = 0;
+    // narrow != nullptr: the run is float64 and is written as float32 (n = source bytes, dst advances half as fast);
+    // *narrow is set when a value does not survive the round trip (the caller then re-sends the chunk as float64)
+    std::atomic<int>* narrow = nullptr;
   };
   explicit CopyPool(int n_threads) {
     for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
@@ -109,7 +112,20 @@ class CopyPool {
       const size_t i = job.next.fetch_add(1);
       if (i >= job.n) return;
       const Task& t = job.tasks[i];
-      for (size_t r = 0; r < t.rows; ++r) memcpy(t.dst + r * t.dpitch, t.src + r * t.spitch, t.n);
+      if (t.narrow) {
+        const double* sp = reinterpret_cast<const double*>(t.src);
+        float* dp = reinterpret_cast<float*>(t.dst);
+        const size_t count = t.n / 8;
+        int lossy = 0;
+        for (size_t k = 0; k < count; ++k) {
+          const float f = static_cast<float>(sp[k]);
+          dp[k] = f;
+          lossy |= static_cast<double>(f) != sp[k];  // also true for NaN: such chunks travel as float64
+        }
+        if (lossy) t.narrow->store(1, std::memory_order_relaxed);
+      } else {
+        for (size_t r = 0; r < t.rows; ++r) memcpy(t.dst + r * t.dpitch, t.src + r * t.spitch, t.n);
+      }
       if (job.done.fetch_add(1) + 1 == job.n) {
         std::lock_guard<std::mutex> g(mu_);
         cv_done_.notify_all();
@@ -633,12 +649,17 @@ static bool lossy_capable(int dtype) { return dtype == UML_F64 || dtype == UML_I
 // gather tasks for rows [r0, r0+rows) of the host source into a compact chunk (row-major [rows][F] or feature-major
 // [F][rows]) at `dst`; contiguous runs are cut into <= 1 MiB pieces so the pool's threads share them
 static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, const void* host, const SrcLayout& L,
-                               int64_t r0, int64_t rows, int F) {
+                               int64_t r0, int64_t rows, int F, std::atomic<int>* narrow = nullptr) {
   tasks.clear();
   const char* src = (const char*)host;
   const size_t piece = 1u << 20;
+  // narrow (float64 source only, contiguous runs): the destination holds float32, so it advances half as fast
   auto add_run = [&](char* d, const char* s_, size_t n) {
-    for (size_t o = 0; o < n; o += piece) tasks.push_back({d + o, s_ + o, std::min(piece, n - o)});
+    for (size_t o = 0; o < n; o += piece) {
+      CopyPool::Task t{d + (narrow ? o / 2 : o), s_ + o, std::min(piece, n - o)};
+      t.narrow = narrow;
+      tasks.push_back(t);
+    }
   };
   if (!L.feature_major) {
     const size_t width = (size_t)F * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
@@ -654,7 +675,8 @@ static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, co
     }
   } else {
     const size_t run = (size_t)rows * L.elem, spitch = (size_t)L.pitch_elems * L.elem;
-    for (int f = 0; f < F; ++f) add_run(dst + (size_t)f * run, src + (size_t)f * spitch + (size_t)r0 * L.elem, run);
+    for (int f = 0; f < F; ++f)
+      add_run(dst + (size_t)f * (narrow ? run / 2 : run), src + (size_t)f * spitch + (size_t)r0 * L.elem, run);
   }
 }
 
@@ -1377,6 +1399,8 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
   bool used[3] = {false, false, false};
   int slot = 0;
   std::vector<CopyPool::Task> tasks;
+  bool wire_f32 = bounce && !direct && src_dtype == UML_F64 && (L.feature_major || L.pitch_elems == F) &&
+                  !getenv("UML_B200_NO_NARROW");
   // UML_B200_PROFILE_HOST=1: host-side seconds per phase of this call on stderr (diagnostics, not a product feature)
   static const bool prof = getenv("UML_B200_PROFILE_HOST") != nullptr;
   double t_wait = 0, t_gather = 0, t_enqueue = 0;
@@ -1397,6 +1421,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     float* xc = e->d_xchunk[slot];
     void* raw = direct ? (void*)xc : e->d_chunk[slot];
     const int tli = (prof && tl_n < kTl) ? tl_n++ : -1;
+    bool chunk_narrow = false;  // this chunk crossed PCIe as fp32 (lossless float64 source)
     // (1) H2D on the copy stream, once the previous user of this slot has finished scoring (the re-score reads the
     //     raw chunk, so that includes it)
     if (used[slot]) HOST_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[3 + slot], 0));
@@ -1415,14 +1440,33 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
           const size_t total = (size_t)rows * ld * 4, piece = 1u << 20;
           for (size_t o = 0; o < total; o += piece)
             tasks.push_back({(char*)e->h_bounce[slot] + o, src0 + o, std::min(piece, total - o)});
-        } else {
-          build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F);
         }
         auto t2 = now();
-        e->pool->run(tasks);
+        if (direct) {
+          e->pool->run(tasks);
+        } else {
+          // float64 frames whose values are exactly representable in fp32 (integer / pixel domains) cross PCIe as fp32:
+          // the gather threads convert while they copy and check every value; the first chunk that is not lossless
+          // (and every chunk after it) travels as float64, as before
+          chunk_narrow = wire_f32;
+          if (chunk_narrow) {
+            std::atomic<int> lossy{0};
+            build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F, &lossy);
+            e->pool->run(tasks);
+            if (lossy.load()) {
+              wire_f32 = false;
+              chunk_narrow = false;
+            }
+          }
+          if (!chunk_narrow) {
+            build_gather_tasks(tasks, (char*)e->h_bounce[slot], host_ptr, L, r0, rows, F);
+            e->pool->run(tasks);
+          }
+        }
         auto t3 = now();
         t_gather += secs(t2, t3);
-        HOST_CUDA(cudaMemcpyAsync(raw, e->h_bounce[slot], (size_t)(rows * wire_row_bytes), cudaMemcpyHostToDevice, e->copy_stream));
+        HOST_CUDA(cudaMemcpyAsync(raw, e->h_bounce[slot], (size_t)(rows * (chunk_narrow ? wire_row_bytes / 2 : wire_row_bytes)),
+                                  cudaMemcpyHostToDevice, e->copy_stream));
         t_enqueue += secs(t3, now());
       } else if (direct) {
         HOST_CUDA(cudaMemcpyAsync(xc, (const char*)host_ptr + (size_t)r0 * ld * 4, (size_t)rows * ld * 4,
@@ -1431,7 +1475,7 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
         HOST_CUDA(copy_chunk_h2d(raw, host_ptr, L, r0, rows, F, e->copy_stream));
       }
     }
-    h2d += rows * wire_row_bytes;
+    h2d += rows * (chunk_narrow ? wire_row_bytes / 2 : wire_row_bytes);
     if (tli >= 0) cudaEventRecord(tl[tli][1], e->copy_stream);
     HOST_CUDA(cudaEventRecord(e->chunk_ev[slot], e->copy_stream));
     HOST_CUDA(cudaStreamWaitEvent(cs, e->chunk_ev[slot], 0));
@@ -1439,8 +1483,8 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     // (2) transpose / down-cast (+ finiteness) on the compute stream
     if (!direct) {
       NvtxRange r_stage("uml:stage_convert");
-      HOST_CUDA(uml::launch_stage_convert(raw, src_dtype, L.feature_major, L.feature_major ? rows : F, rows, F, xc, ld,
-                                          nullptr, 0, e->d_stage, true, cs));
+      HOST_CUDA(uml::launch_stage_convert(raw, chunk_narrow ? (int)UML_F32 : src_dtype, L.feature_major,
+                                          L.feature_major ? rows : F, rows, F, xc, ld, nullptr, 0, e->d_stage, true, cs));
       launches += 1;
     } else if (!exact) {
       HOST_CUDA(uml::launch_finite_scan(xc, ld, rows, F, e->d_stage, cs));
@@ -1454,7 +1498,8 @@ static int predict_host_impl(uml_engine* e, const uml_model* m, const void* host
     l.ld = ld;
     l.n_rows = rows;
     l.labels = e->d_labels + (int64_t)slot * chunk_rows;
-    if (!mlp && exact && !direct && lossy_capable(src_dtype)) {  // (the reference MLP predictor casts features to float32)
+    if (!mlp && exact && !direct && !chunk_narrow && lossy_capable(src_dtype)) {  // (the reference MLP predictor casts to
+      // float32; a chunk that travelled as fp32 was checked lossless on the host: its fp32 rows ARE the caller's values)
       // flagged rows are re-scored from the caller's own values (the raw chunk is still resident): float64 / int
       // features that do not survive the fp32 down-cast still get sklearn's float64 labels (_base.py:366-396)
       l.src.base = raw;
