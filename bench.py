@@ -294,7 +294,9 @@ def cpu_reference_predict_rows_per_s(cfg, arrs, sample_rows: int, repeats: int):
         model_object = est
     spec = opath.PathSpec(reader=reader, targets=["target"], predictor=predictor, model_object=model_object)
     times = []
+    out = None
     for _ in range(repeats):
+        out = None  # the previous step's list is released outside the timed region (both arms do this)
         t0 = time.perf_counter()
         out = opath.predict(spec, features=frame)
         times.append(time.perf_counter() - t0)
@@ -748,6 +750,7 @@ def run_e2e_legs(args, cfg, arrs, eng, model, torch, dist, dev, rank, world, lo,
     app.artifact = ModelArtifact(model_object)
     api_t, out = [], None
     for i in range(args.e2e_steps + 1):
+        out = None  # the previous step's list is released outside the timed region (both arms do this)
         barrier()
         t0 = time.perf_counter()
         out = app.predict(features=frame)
@@ -760,6 +763,9 @@ def run_e2e_legs(args, cfg, arrs, eng, model, torch, dist, dev, rank, world, lo,
     if not np.array_equal(got, want):
         raise SystemExit("bench: Model.predict(features=frame) labels differ from the resident path's")
     api_s = statistics.mean(api_t)
+    from unionml_b200.predictors import last_call_stats
+
+    api_stats = last_call_stats()
 
     # engine leg (round-1 e2e): pinned fp32 rows -> int32 labels in pinned memory
     eng_s, eng_stats = None, None
@@ -793,13 +799,17 @@ def run_e2e_legs(args, cfg, arrs, eng, model, torch, dist, dev, rank, world, lo,
     total = e2e_rows * world
     e2e = {
         "value": total / api_s, "unit": UNIT,
-        "h2d_bytes_per_step": int(e2e_rows * F * 8) * world,   # the float64 block crosses PCIe as is
-        "d2h_bytes_per_step": int(e2e_rows * (8 if kind == "linear" else 4)) * world,
+        # bytes that crossed PCIe, from the engine's own counters of the last call (the digits frame is integer-valued
+        # float64: the gather threads narrow it to fp32 after checking every value; labels come back as int32)
+        "h2d_bytes_per_step": int(api_stats.get("h2d_bytes", e2e_rows * F * 8)) * world,
+        "d2h_bytes_per_step": int(api_stats.get("d2h_bytes", e2e_rows * 4)) * world,
+        "source_bytes_per_step": int(e2e_rows * F * 8) * world,
         "ms_per_step": api_s * 1e3, "steps": args.e2e_steps, "rows_per_step": total,
         "path": "float64 feature-major pandas DataFrame (pageable) -> Model.predict(features=frame) -> @model.predictor "
                 + ("mlp_argmax" if kind == "mlp" else "linear_argmax")
-                + " -> host threads gather chunks into pinned bounce buffers -> H2D -> GPU transpose/down-cast -> scoring "
-                "kernel (+fp64 re-score from the float64 values) -> classes_.take on the device -> D2H float64 -> List[float]",
+                + " -> host threads gather chunks into pinned bounce buffers (float64 -> fp32 when every value of the chunk "
+                "survives it) -> H2D -> GPU transpose/down-cast -> scoring kernel (+fp64 re-score) -> D2H int32 labels -> "
+                "List[float] filled from the class table while the batch is in flight",
         "sample": None if cfg["data"] == "digits" else f"{e2e_rows} rows of each rank's shard per step (the 50M x 784 batch does not fit in host memory)",
     }
     if eng_s is not None:

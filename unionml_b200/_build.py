@@ -34,7 +34,7 @@ def nvcc() -> str:
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))  # .cpp: host-only helpers (g++ through nvcc)
 
 
 def _stale(out: Path, deps) -> bool:

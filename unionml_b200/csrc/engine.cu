@@ -60,6 +60,10 @@ struct HostMirror {  // pinned; device counters are copied here
 
 // Host threads that gather a pageable source chunk into a pinned bounce buffer: cudaMemcpy from pageable memory is
 // staged by the driver on one thread; a few threads doing plain memcpy into page-locked memory keep the link busy.
+namespace uml {
+int narrow_f64_to_f32(const double* src, float* dst, size_t n);  // host_narrow.cpp
+}
+
 class CopyPool {
  public:
   struct Task {  // `rows` runs of n bytes (rows == 1: one contiguous run)
@@ -113,16 +117,9 @@ class CopyPool {
       if (i >= job.n) return;
       const Task& t = job.tasks[i];
       if (t.narrow) {
-        const double* sp = reinterpret_cast<const double*>(t.src);
-        float* dp = reinterpret_cast<float*>(t.dst);
-        const size_t count = t.n / 8;
-        int lossy = 0;
-        for (size_t k = 0; k < count; ++k) {
-          const float f = static_cast<float>(sp[k]);
-          dp[k] = f;
-          lossy |= static_cast<double>(f) != sp[k];  // also true for NaN: such chunks travel as float64
-        }
-        if (lossy) t.narrow->store(1, std::memory_order_relaxed);
+        // (also "lossy" for NaN: such chunks travel as float64 and the staging kernel reports them)
+        if (uml::narrow_f64_to_f32(reinterpret_cast<const double*>(t.src), reinterpret_cast<float*>(t.dst), t.n / 8))
+          t.narrow->store(1, std::memory_order_relaxed);
       } else {
         for (size_t r = 0; r < t.rows; ++r) memcpy(t.dst + r * t.dpitch, t.src + r * t.spitch, t.n);
       }

@@ -170,7 +170,18 @@ def last_ambiguous_rows() -> int:
     return _ambiguous["last"]
 
 
+_last_stats: dict = {}
+
+
+def last_call_stats() -> dict:
+    """The engine's counters of this process's most recent predictor call (path taken, flagged rows, bytes that really
+    crossed PCIe in each direction, kernel launches): what ``bench.py`` reports for the API-level e2e leg."""
+    return dict(_last_stats)
+
+
 def _note_ambiguous(stats) -> None:
+    _last_stats.clear()
+    _last_stats.update(stats or {})
     n = int(stats.get("n_ambiguous", 0)) if stats else 0
     _ambiguous["last"] = n
     if n:
@@ -313,5 +324,6 @@ def mlp_argmax(module: Any, features: Any) -> List[float]:
     dm = device_mlp(module, engine)
     arr = features.to_numpy() if hasattr(features, "to_numpy") else np.asarray(features)
     _check_min_samples(arr)
-    out, _stats = engine.predict_host_list(dm, arr, dm.class_table, exact=_exact_default())
+    out, stats = engine.predict_host_list(dm, arr, dm.class_table, exact=_exact_default())
+    _note_ambiguous(stats)
     return out
