@@ -570,6 +570,12 @@ def run_gpu_arm(args, cfg):
         k_ms.append(st["kernel_ms"])
         r_ms.append(st["recheck_ms"])
         flagged, launches_per_step, path = st["n_flagged"], st["kernel_launches"], st["path"]
+    # this repo's kernels per step: the scoring launches the library reports, plus its label-push copy kernel where the
+    # exchange uses one (push: 1; push4: 4 sub-batches, each scored and pushed); torch's barrier / NCCL are not counted
+    if chosen == "push":
+        launches_per_step += 1
+    elif chosen == "push4":
+        launches_per_step = 4 * (launches_per_step + 1)
     kernel_ms = statistics.mean(k_ms)
     if kind == "mlp" and path != 5:
         raise SystemExit(f"bench: cfg5 must run the tensor-core kernel (stats path 5), got path {path}")
