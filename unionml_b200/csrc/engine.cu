@@ -17,6 +17,7 @@
 #include <sched.h>
 
 #include "uml_common.cuh"
+#include "mlp_rescore.cuh"
 
 // NVTX ranges around the phases of a call (stage / score / re-score / exchange); free when no tool is attached
 struct NvtxRange {
@@ -1766,14 +1767,8 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
     bmax = fmaxf(bmax, fabsf(b2[c]));
   }
   b2p[C] = bmax;
-  std::vector<double> w64((size_t)H * F + H + (size_t)C * H + C);
-  double* q = w64.data();
-  // W1 feature-major [F][H] for the fp64 re-score: lane n reads w1t[f][n], consecutive doubles across the warp
-  for (int f = 0; f < F; ++f)
-    for (int n = 0; n < H; ++n) *q++ = w1[(size_t)n * F + f];
-  for (int i = 0; i < H; ++i) *q++ = b1[i];
-  for (size_t i = 0; i < (size_t)C * H; ++i) *q++ = w2[i];
-  for (int i = 0; i < C; ++i) *q++ = b2[i];
+  // fp64 operands of the re-score, laid out as the kernels keep them in shared memory
+  const std::vector<double> w64 = uml::mlp_rs_build_pack(w1, b1, w2, b2, F, H, C);
 
   uml_mlp* m = new uml_mlp();
   m->e = e;
@@ -1803,10 +1798,7 @@ int uml_mlp_load(uml_engine* e, uml_mlp** out, const float* w1, const float* b1,
   m->dm.b1 = m->d_b1;
   m->dm.w2t = m->d_w2t;
   m->dm.b2 = m->d_b2;
-  m->dm.w1_64 = m->d_w64;
-  m->dm.b1_64 = m->d_w64 + (size_t)H * F;
-  m->dm.w2_64 = m->dm.b1_64 + H;
-  m->dm.b2_64 = m->dm.w2_64 + (size_t)C * H;
+  m->dm.rs_pack = m->d_w64;
   m->dm.n_in = F;
   m->dm.n_hidden = H;
   m->dm.n_classes = C;

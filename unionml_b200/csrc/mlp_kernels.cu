@@ -269,10 +269,7 @@ struct MlpRescoreParams {
   const float* x;
   long long ld;
   long long n_rows;
-  const double* w1;  // [F][H]
-  const double* b1;
-  const double* w2;  // [C][H]
-  const double* b2;
+  const double* pack;  // the shared-memory image of the fp64 operands (mlp_rs_build_pack)
   int F, H, C;
   const int* flag_count;
   const int32_t* flag_rows;
@@ -286,38 +283,59 @@ struct MlpRescoreParams {
   unsigned long long* counters;
 };
 
-// Shared-memory version (mlp_rescore.cuh): W1 (fp64, [F][H]), W2 ([C][H+1], padded rows), the biases and two bound
-// vectors are staged once per block; per row the warp loads x with one coalesced access, keeps it (as doubles) and the
-// hidden activations in its own shared-memory strip, and every inner-loop operand is a broadcast / conflict-free LDS.
-// Layer 1: lane per hidden unit, four independent fp64 chains over the features.  Layer 2: lane per class (no warp
-// reductions), then one butterfly for arg-max and runner-up.
+constexpr int kMlpRsRows = 4;  // rows per warp pass (mlp_rescore.cuh: shared-memory wavefronts per row fall 3 -> 1)
+
+// Shared-memory version (mlp_rescore.cuh): the fp64 image of the model (W1 [F][H], W2 [C][H+1], biases, bound vectors;
+// built on the host at load) is copied once per block; a warp scores four rows per pass - their features and hidden
+// activations interleaved in the warp's own strip, so every W element it reads from shared memory is used four times.
+// Layer 1: lane per hidden unit.  Layer 2: lane per class (no warp reductions), then one butterfly per row for arg-max
+// and runner-up.
 __global__ void __launch_bounds__(256) mlp_rescore_f64_kernel(const MlpRescoreParams p) {
-  extern __shared__ double rs_smem[];
+  extern __shared__ __align__(16) double rs_smem[];
+  constexpr int R = kMlpRsRows;
   // (weights are staged first: they do not depend on the scoring kernel; the flag list does - see the wait below)
-  MlpRsView view = mlp_rs_stage(rs_smem, p.w1, p.b1, p.w2, p.b2, p.F, p.H, p.C);
+  MlpRsView view = mlp_rs_stage(rs_smem, p.pack, p.F, p.H, p.C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* xs = rs_smem + mlp_rs_weight_doubles(p.F, p.H, p.C) + warp * mlp_rs_strip_doubles(p.F, p.H);
-  double* hv = xs + p.F;
+  double* xs = rs_smem + mlp_rs_weight_doubles(p.F, p.H, p.C) + warp * mlp_rs_strip_doubles(p.F, p.H, R);
+  double* hv = xs + p.F * R;
   __syncthreads();
   mlp_rs_finish_stage(view);
-  __syncthreads();
 
   pdl_wait_for_predecessor();  // from here on: the flag list and labels of the scoring kernel this launch depends on
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
   if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
-  for (long long i = warp_global; i < n; i += warps_total) {
-    const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
-    const MlpRowResult r = mlp_rs_row(view, p.x + row * p.ld, xs, hv, lane);
-    if (lane == 0) {
-      if (p.labels) p.labels[row] = r.idx;
-      for (int q = 0; q < p.n_peers; ++q) {
-        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + row] = static_cast<uint8_t>(r.idx);
-        else static_cast<int32_t*>(p.peers[q])[p.row_offset + row] = r.idx;
+  // warp w takes entries [w*R, w*R + R) of the list, then strides by all warps: a short list spreads over many warps
+  for (long long i = warp_global * R; i < n; i += warps_total * R) {
+    long long row[R];
+    const float* xr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long j = i + r < n ? i + r : i;  // unused slots repeat the first row (result ignored)
+      row[r] = p.all_rows ? j : static_cast<long long>(p.flag_rows[j]);
+      xr[r] = p.x + row[r] * p.ld;
+    }
+    MlpRowResult res[R];
+    mlp_rs_rows<R>(view, xr, xs, hv, lane, res);
+    if (lane < R && i + lane < n) {
+      // lane r publishes row r (R <= 4 lanes, one per row)
+      long long my_row = row[0];
+      MlpRowResult mine = res[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        if (lane == r) {
+          my_row = row[r];
+          mine = res[r];
+        }
       }
-      if (r.bad) atomicAdd(&p.counters[1], 1ull);
-      if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
+      if (p.labels) p.labels[my_row] = mine.idx;
+      for (int q = 0; q < p.n_peers; ++q) {
+        if (p.wire_u8) static_cast<uint8_t*>(p.peers[q])[p.row_offset + my_row] = static_cast<uint8_t>(mine.idx);
+        else static_cast<int32_t*>(p.peers[q])[p.row_offset + my_row] = mine.idx;
+      }
+      if (mine.bad) atomicAdd(&p.counters[1], 1ull);
+      if (mine.ambiguous) atomicAdd(&p.counters[0], 1ull);
     }
   }
   // hand the flag list back empty (see rescore_f64_kernel in linear_kernels.cu)
@@ -419,10 +437,7 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   p.x = x;
   p.ld = ld;
   p.n_rows = n_rows;
-  p.w1 = m.w1_64;
-  p.b1 = m.b1_64;
-  p.w2 = m.w2_64;
-  p.b2 = m.b2_64;
+  p.pack = m.rs_pack;
   p.F = m.n_in;
   p.H = m.n_hidden;
   p.C = m.n_classes;
@@ -437,7 +452,7 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   p.row_offset = out.row_offset;
   p.counters = flags.counters;
   // shared memory: W1 + padded W2 + biases + the two bound vectors + one strip (x, hidden values) per warp
-  const size_t smem = (mlp_rs_weight_doubles(m.n_in, m.n_hidden, m.n_classes) + 8 * mlp_rs_strip_doubles(m.n_in, m.n_hidden)) * sizeof(double);
+  const size_t smem = (mlp_rs_weight_doubles(m.n_in, m.n_hidden, m.n_classes) + 8 * mlp_rs_strip_doubles(m.n_in, m.n_hidden, kMlpRsRows)) * sizeof(double);
   if (smem > static_cast<size_t>(kMaxSmemBytes)) return cudaErrorInvalidValue;  // uml_mlp_load bounds F * H
   static size_t configured = 0;
   if (smem > configured) {
@@ -448,7 +463,7 @@ cudaError_t launch_mlp_rescore_f64(const MlpDeviceModel& m, const float* x, int6
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_rescore_f64_kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long blocks = static_cast<long long>(sm_count) * per_sm;  // persistent: every resident warp loops over rows
-  if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 7) / 8);
+  if (all_rows) blocks = std::min<long long>(blocks, (n_rows + 8 * kMlpRsRows - 1) / (8 * kMlpRsRows));
   cudaError_t lerr = launch_dependent(mlp_rescore_f64_kernel, static_cast<int>(std::max<long long>(1, blocks)), 256, smem, stream, p);
   if (lerr != cudaSuccess) return lerr;
   return cudaGetLastError();

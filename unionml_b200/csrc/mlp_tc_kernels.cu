@@ -87,10 +87,7 @@ struct MlpTcParams {
   const float* x;
   long long ld;
   int n_in;
-  const double* w1_64;  // [F][H]
-  const double* b1_64;
-  const double* w2_64;  // [C][H]
-  const double* b2_64;
+  const double* rs_pack;  // shared-memory image of the fp64 operands (mlp_rs_build_pack)
   unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] re-scored rows
 };
 
@@ -130,7 +127,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   // warps done, 3 slots consumed), then the fp64 weights and one strip per epilogue / re-score warp
   int* q_slots = reinterpret_cast<int*>(tmem_base_s + 4);
   int* q_ctl = q_slots + kTcQueueCap;
-  double* rs_area = reinterpret_cast<double*>(q_ctl + 4);
+  double* rs_area = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(q_ctl + 4) + 15u) & ~static_cast<uintptr_t>(15));  // 16-byte copies
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,7 +142,7 @@ mlp_argmax_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   MlpRsView rs_view{};
   if constexpr (EXACT && QUEUE) {
     for (int i = threadIdx.x; i < kTcQueueCap + 4; i += blockDim.x) q_slots[i] = 0;
-    rs_view = mlp_rs_stage(rs_area, p.w1_64, p.b1_64, p.w2_64, p.b2_64, p.n_in, H, C);
+    rs_view = mlp_rs_stage(rs_area, p.rs_pack, p.n_in, H, C);
     __syncthreads();
     mlp_rs_finish_stage(rs_view);
   }
@@ -570,10 +567,7 @@ static cudaError_t mlp_tc_launch_one(const CUtensorMap& xmap, const MlpDeviceMod
   p.x = l.x;
   p.ld = l.ld;
   p.n_in = m.n_in;
-  p.w1_64 = m.w1_64;
-  p.b1_64 = m.b1_64;
-  p.w2_64 = m.w2_64;
-  p.b2_64 = m.b2_64;
+  p.rs_pack = m.rs_pack;
   p.counters = flags.counters;
   const size_t fixed = mlp_tc_fixed_smem(m, QUEUE);
   int stages = static_cast<int>((static_cast<size_t>(kMaxSmemBytes) - fixed) / kStageBytes);

@@ -119,10 +119,7 @@ struct MlpDeviceModel {
   const float* b1;   // [H + 4], entry H = max_n |b1_n|
   const float* w2t;  // [H][cp], column C = max_c |w2_cn|
   const float* b2;   // [cp], entry C = max_c |b2_c|
-  const double* w1_64;  // [F][H] feature-major (coalesced across the warp's hidden units in the re-score kernel)
-  const double* b1_64;
-  const double* w2_64;  // [C][H]
-  const double* b2_64;
+  const double* rs_pack;  // fp64 operands of the re-score as one shared-memory image (mlp_rescore.cuh: mlp_rs_build_pack)
   int n_in, n_hidden, n_classes;
   int cp, f_pad;
   double w2_abs_row_sum_max;  // max_c sum_n |w2_cn|
