@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--what", required=True, choices=["linear", "mlp", "stage", "small"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--chunk-rows", type=int, default=0, help="stage: run the staging kernels on chunks of this many rows "
+                    "(through predict_host) instead of stage()'s default 64 MiB chunks")
     args = ap.parse_args()
     import torch
 
@@ -45,12 +47,19 @@ def main():
         rows = min(rows, 4_000_000)
         src = eng.pinned_empty((64, rows), np.float64)  # feature-major float64: a pandas block
         src[:] = np.random.default_rng(0).integers(0, 17, size=(64, rows))
-        for _ in range(args.reps):
-            eng.stage(src.T).free()                      # stage_featmajor_kernel<double>
         rm = eng.pinned_empty((rows, 64), np.float64)
         rm[:] = src.T
-        for _ in range(args.reps):
-            eng.stage(rm).free()                         # stage_dense_kernel<double>
+        if args.chunk_rows:
+            z = np.load(ROOT / "tests" / "golden" / "digits_lr.npz")
+            m = eng.load_linear(z["coef"], z["intercept"])
+            for _ in range(args.reps):
+                eng.predict_host(m, src.T, exact=True, chunk_rows=args.chunk_rows)   # stage_featmajor_kernel<double>
+                eng.predict_host(m, rm, exact=True, chunk_rows=args.chunk_rows)      # stage_dense_kernel<double>
+        else:
+            for _ in range(args.reps):
+                eng.stage(src.T).free()                      # stage_featmajor_kernel<double>
+            for _ in range(args.reps):
+                eng.stage(rm).free()                         # stage_dense_kernel<double>
     else:
         z = np.load(ROOT / "tests" / "golden" / "digits_lr.npz")
         m = eng.load_linear(z["coef"], z["intercept"])
