@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--what", required=True, choices=["linear", "mlp", "stage", "small"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--features", type=int, default=64, help="linear: 784 = the cfg-3 shape (random weights, pixel / 255 rows)")
     ap.add_argument("--chunk-rows", type=int, default=0, help="stage: run the staging kernels on chunks of this many rows "
                     "(through predict_host) instead of stage()'s default 64 MiB chunks")
     args = ap.parse_args()
@@ -32,7 +33,16 @@ def main():
         X = torch.randint(0, 17, (rows, 64), device=dev, dtype=torch.int32).to(torch.float32)
         b = eng.wrap_device(X.data_ptr(), rows, 64, keepalive=X)
         lab = torch.empty(rows, dtype=torch.uint8, device=dev)
-        if args.what == "linear":
+        if args.what == "linear" and args.features != 64:
+            F = args.features
+            rng = np.random.default_rng(3)
+            m = eng.load_linear(rng.standard_normal((10, F)) * 0.05, rng.standard_normal(10))
+            X = (torch.randint(0, 256, (rows, F), device=dev, dtype=torch.int32).to(torch.float32) / 255.0).contiguous()
+            b = eng.wrap_device(X.data_ptr(), rows, F, keepalive=X)
+            for _ in range(args.reps):
+                st = eng.predict_peers(m, b, [lab.data_ptr()], 0, exact=True, want_stats=True, label_bytes=1)
+            print(st)
+        elif args.what == "linear":
             z = np.load(ROOT / "tests" / "golden" / "digits_lr.npz")
             m = eng.load_linear(z["coef"], z["intercept"])
             for _ in range(args.reps):

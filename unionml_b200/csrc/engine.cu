@@ -454,16 +454,22 @@ static int upload_model(uml_engine* e, uml_model* m, const std::vector<double>& 
   };
   UML_CUDA(e, ensure((void**)&m->d_wt, wt.size() * 4));
   UML_CUDA(e, ensure((void**)&m->d_bias, bias.size() * 4));
-  UML_CUDA(e, ensure((void**)&m->d_w64, w.size() * 8));
+  // fp64 weights feature-major: w64t[f][stride], the classes of one feature contiguous (zero padded)
+  const int stride = uml::linear_w64_stride(C);
+  std::vector<double> w64t((size_t)F * stride, 0.0);
+  for (int c = 0; c < C; ++c)
+    for (int f = 0; f < F; ++f) w64t[(size_t)f * stride + c] = w[(size_t)c * F + f];
+  UML_CUDA(e, ensure((void**)&m->d_w64, w64t.size() * 8));
   UML_CUDA(e, ensure((void**)&m->d_b64, b.size() * 8));
   UML_CUDA(e, cudaMemcpy(m->d_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
   UML_CUDA(e, cudaMemcpy(m->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
-  UML_CUDA(e, cudaMemcpy(m->d_w64, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+  UML_CUDA(e, cudaMemcpy(m->d_w64, w64t.data(), w64t.size() * 8, cudaMemcpyHostToDevice));
   UML_CUDA(e, cudaMemcpy(m->d_b64, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
   m->dm.wt = m->d_wt;
   m->dm.bias = m->d_bias;
   m->dm.w64 = m->d_w64;
   m->dm.b64 = m->d_b64;
+  m->dm.w64_stride = stride;
   m->dm.cp = cp;
   m->dm.f_pad = f_pad;
   m->uid = g_model_uid.fetch_add(1);

@@ -46,30 +46,48 @@ struct RowScore {
 };
 
 // float64 scores of one row by one warp, first maximum wins like np.argmax.  Lanes split the features; classes are
-// scored sixteen at a time (each feature value is loaded once per round, 32 independent fp64 chains per lane), the
-// sixteen sums are reduced with warp_reduce16 and the arg-max / runner-up found by a butterfly over the lanes.
-// LOAD(f) yields feature f of the row as double.
+// scored sixteen at a time (32 independent fp64 chains per lane), the sixteen sums are reduced with warp_reduce16 and
+// the arg-max / runner-up found by a butterfly over the lanes.  LOAD(f) yields feature f of the row as double.
+// w64 is feature-major, w64[f * S + c]: a lane fetches the classes of its feature with 16-byte loads off ONE address
+// (immediate offsets) - the class-major table this replaces cost a 64-bit multiply-add per weight, 52 % of the kernel's
+// instructions at F = 784 (profiles/r02_rescore_f64_f784_before.*).
 template <typename LOAD>
-__device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, const double* __restrict__ b64,
-                                                  int F, int C, int lane) {
+__device__ __forceinline__ RowScore score_row_f64(LOAD load, const double* __restrict__ w64, int S,
+                                                  const double* __restrict__ b64, int F, int C, int lane) {
   const double u = 1.1102230246251565e-16;  // 2^-53
   bool bad = false;
   double best = 0.0, second = -INFINITY, amax = 0.0;
   int idx = 0;
   for (int c0 = 0; c0 < C; c0 += 16) {
+    const int pairs = min(8, (C - c0 + 1) / 2);  // 16-byte loads per feature this round (an odd C ends in a zero pad)
     double s[16], a[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) s[q] = a[q] = 0.0;
-    for (int f = lane; f < F; f += 32) {
-      const double xv = load(f);
-      if (!isfinite(xv)) bad = true;
-      const double ax = fabs(xv);
+    // the row's features come from global memory (or, on the online path, over PCIe): four loads are issued before the
+    // first is used, otherwise every 32-feature step of a wide model (F = 784: 25 steps) waits a full round trip
+    constexpr int XB = 4;
+    for (int f0 = lane; f0 < F; f0 += 32 * XB) {
+      double xb[XB];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        if (c0 + q < C) {
-          const double w = w64[static_cast<long long>(c0 + q) * F + f];
-          s[q] = fma(xv, w, s[q]);
-          a[q] = fma(ax, fabs(w), a[q]);
+      for (int k = 0; k < XB; ++k) xb[k] = f0 + 32 * k < F ? load(f0 + 32 * k) : 0.0;
+#pragma unroll
+      for (int k = 0; k < XB; ++k) {
+        const int f = f0 + 32 * k;
+        if (f < F) {
+          const double xv = xb[k];
+          if (!isfinite(xv)) bad = true;
+          const double ax = fabs(xv);
+          const double2* wp = reinterpret_cast<const double2*>(w64 + static_cast<size_t>(f) * S + c0);
+#pragma unroll
+          for (int q2 = 0; q2 < 8; ++q2) {
+            if (q2 < pairs) {
+              const double2 w = wp[q2];
+              s[2 * q2] = fma(xv, w.x, s[2 * q2]);
+              a[2 * q2] = fma(ax, fabs(w.x), a[2 * q2]);
+              s[2 * q2 + 1] = fma(xv, w.y, s[2 * q2 + 1]);
+              a[2 * q2 + 1] = fma(ax, fabs(w.y), a[2 * q2 + 1]);
+            }
+          }
         }
       }
     }
@@ -130,8 +148,9 @@ struct TmaKernelParams {
   const double* x64;
   SrcView src;
   long long ld, ld64;
-  const double* w64;
+  const double* w64;  // [F][w64_stride], feature-major
   const double* b64;
+  int w64_stride;
   int n_classes, n_features;
   unsigned long long* counters;  // [0] ambiguous, [1] nonfinite, [2] re-scored rows
 };
@@ -141,13 +160,13 @@ __device__ __noinline__ int rescore_row_inline(const TmaKernelParams& p, long lo
   RowScore r;
   if (p.src.base) {
     const SrcView v = p.src;
-    r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+    r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.w64_stride, p.b64, p.n_features, p.n_classes, lane);
   } else if (p.x64) {
     const double* xr64 = p.x64 + row * p.ld64;
-    r = score_row_f64([&](int f) { return xr64[f]; }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+    r = score_row_f64([&](int f) { return xr64[f]; }, p.w64, p.w64_stride, p.b64, p.n_features, p.n_classes, lane);
   } else {
     const float* xr = p.x + row * p.ld;
-    r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+    r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, p.w64, p.w64_stride, p.b64, p.n_features, p.n_classes, lane);
   }
   if (lane == 0) {
     if (r.bad) atomicAdd(&p.counters[1], 1ull);
@@ -520,8 +539,9 @@ struct RescoreParams {
   SrcView src;
   long long ld, ld64;
   long long n_rows;
-  const double* w64;
+  const double* w64;  // [F][w64_stride], feature-major
   const double* b64;
+  int w64_stride;
   int n_classes, n_features;
   const int* flag_count;
   const int32_t* flag_rows;
@@ -537,40 +557,23 @@ struct RescoreParams {
 };
 
 
-__global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
-  // W (fp64, [C][F]) and b are staged in shared memory when they fit (p.smem_weights): a wide model (784 x 10 = 62 KB)
-  // would otherwise be re-read from L2 for every re-scored row - 8 600 rows x 62 KB = 0.5 GB per cfg-3 step
-  extern __shared__ double rs_w[];
-  const double* w64 = p.w64;
-  const double* b64 = p.b64;
-  if (p.smem_weights) {
-    const int nw = p.n_classes * p.n_features;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) rs_w[i] = p.w64[i];
-    for (int i = threadIdx.x; i < p.n_classes; i += blockDim.x) rs_w[nw + i] = p.b64[i];
-    w64 = rs_w;
-    b64 = rs_w + nw;
-    __syncthreads();
-  }
-  pdl_wait_for_predecessor();  // the flag list is written by the scoring kernel this launch depends on
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
-  const int F = p.n_features, C = p.n_classes;
-  if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
-
+// rows [warp_global, n) step warps_total of the flag list (or of the batch), one warp per row
+template <typename WPTR>
+__device__ __forceinline__ void rescore_rows(const RescoreParams& p, WPTR w64, WPTR b64, long long n, int lane,
+                                             long long warp_global, long long warps_total) {
+  const int F = p.n_features, C = p.n_classes, S = p.w64_stride;
   for (long long i = warp_global; i < n; i += warps_total) {
     const long long row = p.all_rows ? i : static_cast<long long>(p.flag_rows[i]);
     RowScore r;
     if (p.src.base) {
       const SrcView v = p.src;
-      r = score_row_f64([&](int f) { return load_src(v, row, f); }, w64, b64, F, C, lane);
+      r = score_row_f64([&](int f) { return load_src(v, row, f); }, w64, S, b64, F, C, lane);
     } else if (p.x64) {
       const double* xr64 = p.x64 + row * p.ld64;
-      r = score_row_f64([&](int f) { return xr64[f]; }, w64, b64, F, C, lane);
+      r = score_row_f64([&](int f) { return xr64[f]; }, w64, S, b64, F, C, lane);
     } else {
       const float* xr = p.x + row * p.ld;
-      r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, w64, b64, F, C, lane);
+      r = score_row_f64([&](int f) { return static_cast<double>(xr[f]); }, w64, S, b64, F, C, lane);
     }
     if (lane == 0) {
       if (p.labels) p.labels[row] = r.idx;
@@ -581,6 +584,33 @@ __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p)
       if (r.bad) atomicAdd(&p.counters[1], 1ull);
       if (r.ambiguous) atomicAdd(&p.counters[0], 1ull);
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p) {
+  // W (fp64, feature-major [F][S]) and b are staged in shared memory when they fit (p.smem_weights): a wide model
+  // (784 x 10 = 62 KB) would otherwise be re-read from L2 for every re-scored row.  Two copies of the row loop so that
+  // the shared-memory one compiles to LDS.128 (a pointer chosen at run time would make every weight load generic).
+  extern __shared__ __align__(16) double rs_w[];
+  const int nw = p.n_features * p.w64_stride;
+  if (p.smem_weights) {
+    const double2* src = reinterpret_cast<const double2*>(p.w64);
+    double2* dst = reinterpret_cast<double2*>(rs_w);
+    for (int i = threadIdx.x; i < nw / 2; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < p.n_classes; i += blockDim.x) rs_w[nw + i] = p.b64[i];
+    __syncthreads();
+  }
+  pdl_wait_for_predecessor();  // the flag list is written by the scoring kernel this launch depends on
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long n = p.all_rows ? p.n_rows : static_cast<long long>(min(*p.flag_count, p.flag_cap));
+  if (!p.all_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.counters[2], static_cast<unsigned long long>(n));
+  if (p.smem_weights) {
+    const double* ws = rs_w;
+    rescore_rows(p, ws, ws + nw, n, lane, warp_global, warps_total);
+  } else {
+    rescore_rows(p, p.w64, p.b64, n, lane, warp_global, warps_total);
   }
   // hand the flag list back empty: every block has read *flag_count before it gets here, so the last one to finish may
   // reset it (and the ticket) for the next scoring launch on this stream - no memset between steps
@@ -602,8 +632,9 @@ __global__ void __launch_bounds__(256) rescore_f64_kernel(const RescoreParams p)
 // ---------------------------------------------------------------------------------------------------------------
 struct SmallParams {
   SrcView src;
-  const double* w64;
+  const double* w64;  // [F][w64_stride], feature-major
   const double* b64;
+  int w64_stride;
   int n_classes, n_features, n_rows;
   SmallResult* out;
 };
@@ -613,7 +644,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const SmallParams p) 
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= p.n_rows) return;
   const SrcView v = p.src;
-  const RowScore r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.b64, p.n_features, p.n_classes, lane);
+  const RowScore r = score_row_f64([&](int f) { return load_src(v, row, f); }, p.w64, p.w64_stride, p.b64, p.n_features, p.n_classes, lane);
   if (lane == 0) {
     p.out[row].label = r.idx;
     p.out[row].status = (r.bad ? 1 : 0) | (r.ambiguous ? 2 : 0);
@@ -626,6 +657,7 @@ cudaError_t launch_linear_small(const LinearDeviceModel& m, const SrcView& src, 
   SmallParams p{};
   p.src = src;
   p.w64 = m.w64;
+  p.w64_stride = m.w64_stride;
   p.b64 = m.b64;
   p.n_classes = m.n_classes;
   p.n_features = m.n_features;
@@ -809,7 +841,7 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
                               bool* rescore_kernel_needed) {
   // the in-kernel queue re-scores rows with W in global memory / L2: fine for a 5 KB model, not for 62 KB of fp64
   // weights per row (cfg 3) - wide models take the re-score kernel, which stages W in shared memory
-  const bool small_model = static_cast<size_t>(m.n_classes) * m.n_features * sizeof(double) <= 16 * 1024;
+  const bool small_model = static_cast<size_t>(m.w64_stride) * m.n_features * sizeof(double) <= 16 * 1024;
   const bool inline_rescore = exact && small_model && linear_queue_rescore();
   if (rescore_kernel_needed) *rescore_kernel_needed = exact && !inline_rescore;
   if (!linear_tma_supported(m, err)) return cudaErrorInvalidValue;
@@ -844,6 +876,7 @@ cudaError_t launch_linear_tma(const CUtensorMap& xmap, const LinearDeviceModel& 
   p.ld = l.ld;
   p.ld64 = l.ld64;
   p.w64 = m.w64;
+  p.w64_stride = m.w64_stride;
   p.b64 = m.b64;
   p.n_classes = m.n_classes;
   p.n_features = m.n_features;
@@ -867,6 +900,7 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   p.ld64 = l.ld64;
   p.n_rows = l.n_rows;
   p.w64 = m.w64;
+  p.w64_stride = m.w64_stride;
   p.b64 = m.b64;
   p.n_classes = m.n_classes;
   p.n_features = m.n_features;
@@ -881,7 +915,7 @@ cudaError_t launch_rescore_f64(const LinearDeviceModel& m, const LinearLaunch& l
   p.row_offset = l.row_offset;
   p.counters = flags.counters;
   // shared-memory copy of W, b when it fits next to nothing else (<= 200 KB)
-  size_t smem = (static_cast<size_t>(m.n_classes) * m.n_features + m.n_classes) * sizeof(double);
+  size_t smem = (static_cast<size_t>(m.n_features) * m.w64_stride + m.n_classes) * sizeof(double);
   if (smem > 200 * 1024) smem = 0;
   p.smem_weights = smem > 0 ? 1 : 0;
   static size_t configured = 0;

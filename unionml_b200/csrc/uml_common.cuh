@@ -30,14 +30,25 @@ struct LinearDeviceModel {
   // wmax_f = max_c |w_cf| for the error bound), bias[cp] (column C = max_c |b_c|)
   const float* wt;
   const float* bias;
-  // fp64 operands of the re-score / generic kernel: w64[C][F], b64[C]
+  // fp64 operands of the re-score / generic kernel: w64[F][w64_stride] (feature-major, classes contiguous and zero
+  // padded; see linear_w64_stride), b64[C]
   const double* w64;
   const double* b64;
+  int w64_stride;
   int n_classes;   // C after binary expansion (>= 2)
   int n_features;  // F
   int cp;          // padded class columns in wt
   int f_pad;       // rows of wt = 32 * ceil(F / 32), zero padded
 };
+
+// doubles per feature of the fp64 weight table: a lane reads the classes of ITS feature as 16-byte pairs, so the row
+// length in 16-byte units must be odd for the eight lanes of a quarter-warp to land in eight different bank groups of
+// shared memory (C = 10 -> 10 doubles = 80 bytes, C = 16 -> 18, C = 2 -> 2); rounds of 16 classes stay 16-byte aligned
+__host__ __device__ inline int linear_w64_stride(int n_classes) {
+  int pairs = (n_classes + 1) / 2;
+  if (pairs % 2 == 0) pairs += 1;
+  return 2 * pairs;
+}
 
 struct FlagList {
   int* count;        // number of flagged rows appended so far; the re-score kernel's last block resets it to 0
