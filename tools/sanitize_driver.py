@@ -37,4 +37,15 @@ eng.predict_mlp_host(mlp, X.astype(np.float64), chunk_rows=4096)
 eng.predict_host_list(m, X.astype(np.float64), [float(c) for c in range(10)], chunk_rows=4096, asynchronous=True)
 m0 = eng.load_linear(np.zeros((5, 64)), np.zeros(5))    # every row a tie: the queue backs up, scoring warps re-score their own rows
 eng.predict(m0, b, exact=True)
+# fp64 re-score with the feature-major weight table: two rounds of classes (C = 20 -> generic all-rows kernel), an odd
+# class count behind the tile kernel, and a wide model whose table is staged in shared memory (F = 784)
+rng = np.random.default_rng(4)
+m20 = eng.load_linear(rng.standard_normal((20, 64)), rng.standard_normal(20))
+eng.predict(m20, b, exact=True)
+m3 = eng.load_linear(rng.standard_normal((3, 64)), rng.standard_normal(3))
+eng.predict(m3, bf, exact=True)
+X784 = (rng.integers(0, 256, size=(6_001, 784)) / 255.0)
+m784 = eng.load_linear(rng.standard_normal((10, 784)) * 0.05, rng.standard_normal(10))
+eng.predict(m784, eng.stage(X784), exact=True)
+eng.predict_host(m784, X784, exact=True, chunk_rows=2048)
 print("sanitizer driver ok")
