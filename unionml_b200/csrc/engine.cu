@@ -685,11 +685,12 @@ static void build_gather_tasks(std::vector<CopyPool::Task>& tasks, char* dst, co
 }
 
 // CPUs this process can use: scheduler affinity, capped by the cgroup CPU quota (v2 cpu.max, v1 cfs_quota_us)
-static int usable_cpus() {
+static int usable_cpus(int* logical = nullptr) {
   int n = (int)std::thread::hardware_concurrency();
   cpu_set_t set;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
   if (n <= 0) n = 4;
+  if (logical) *logical = n;  // CPUs the scheduler may place threads on (before the quota)
   auto read_two = [](const char* path, long long* a, long long* b) -> bool {
     FILE* f = fopen(path, "r");
     if (!f) return false;
@@ -728,14 +729,19 @@ static int ensure_bounce(uml_engine* e, int64_t bytes) {
   if (!e->pool) {
     int n = 0;
     if (const char* env = getenv("UML_B200_COPY_THREADS")) n = atoi(env);
-    // default: the CPUs this process may really use (affinity and cgroup quota - the GPU boxes give a container 16 of
-    // 128), minus two so that the caller's own thread (Python turning finished chunks into list pieces in the
-    // asynchronous form) never pushes the group over its quota: CFS then throttles every thread for the rest of the period
-    // ... and the CPUs are shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+    // default: sized from the CPU time this process may really use (affinity and cgroup quota - the GPU boxes give a
+    // container a 16-CPU quota on 128 logical CPUs).  The gather threads are stalled on host memory most of the time
+    // and idle between chunks, so 1.5 x the quota is where the 10M x 64 float64 frame gathers fastest on those boxes
+    // (threads: pipeline ms  10: 98, 14: 99, 20: 77-89, 24: 70, 28: 74, 32: 70, 40: 77-116, 56: 133 - past ~2 x the
+    // quota CFS throttles every thread for the rest of the period).  Never more than the logical CPUs minus two (the
+    // caller's thread fills the result list meanwhile), at most 32, and the CPUs are shared by the ranks of this node
+    // (torchrun exports LOCAL_WORLD_SIZE).
     if (n <= 0) {
       int ranks = 1;
       if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lw));
-      n = std::min(16, std::max(1, (usable_cpus() - 2) / ranks));
+      int logical = 0;
+      const int quota = usable_cpus(&logical);
+      n = std::min(32, std::max(1, std::min(logical - 2, quota * 3 / 2) / ranks));
     }
     e->pool = new CopyPool(n - 1);  // the calling thread is the n-th worker
   }
