@@ -43,8 +43,8 @@ CONFIGS = {
         "metric": "rows/sec batch predict (64->10 logistic)", "kind": "linear", "F": 64, "C": 10, "rows": 10_000_000,
         "data": "digits", "kernel": "linear_argmax_tma_kernel<10, EXACT>", "cpu_rows": 2_000_000,
         "what": "BASELINE.json configs[1]: digits predictor (golden LogisticRegression 64->10)",
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch on 10M rows (profiles/r01_linear_argmax_tma.ncu_raw.csv)
-        "traffic_10m": 2_567_349_000, "traffic_src": "profiles/r01_linear_argmax_tma.ncu_raw.csv (ncu --set full, per launch)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch on 10M rows (profiles/r02_linear_argmax_tma_queue.ncu_raw.csv)
+        "traffic_10m": 2_568_923_504, "traffic_src": "profiles/r02_linear_argmax_tma_queue.ncu_raw.csv (ncu --set full, per launch: dram read 2.560358 GB + write 8.565504 MB)",
     },
     "cfg3": {
         "metric": "rows/sec batch predict (784->10 logistic)", "kind": "linear", "F": 784, "C": 10, "rows": 50_000_000,
@@ -56,7 +56,7 @@ CONFIGS = {
         "metric": "rows/sec batch predict (2-layer MLP 64->32->10)", "kind": "mlp", "F": 64, "C": 10, "rows": 10_000_000,
         "data": "digits", "kernel": "mlp_argmax_tc_kernel<32, 10, EXACT> (tcgen05 kind::tf32)", "cpu_rows": 200_000,
         "what": "BASELINE.json configs[4]: PyTorch 2-layer MLP predictor (torch.manual_seed(0) PytorchModel(64, 32, 10))",
-        "traffic_10m": None, "traffic_src": None,
+        "traffic_10m": 2_568_177_568, "traffic_src": "profiles/r02_mlp_argmax_tc.ncu_raw.csv (ncu --set full, per launch: dram read 2.560164 GB + write 8.013568 MB)",
     },
 }
 CHUNK = 1_000_000  # digits rows are generated in global 1M-row chunks: chunk k = default_rng(k)
