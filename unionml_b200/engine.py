@@ -504,16 +504,18 @@ class Engine:
             out: list = [None] * n
             fill(out, 0, n)
             return out, d
-        out = [None] * n
         begin = lib.uml_mlp_predict_host_begin if is_mlp else lib.uml_linear_predict_host_begin
         with self._lock:
+            t0 = time.perf_counter()
             st = begin(self._h, model._h, C.c_void_p(arr.ctypes.data), n, arr.shape[1], arr.strides[0], arr.strides[1],
                        _DTYPES[arr.dtype], labels.ctypes.data_as(C.c_void_p), mode, chunk_rows)
             self._check(st)
             done, rows_done, finished = 0, C.c_int64(), C.c_int()
-            t0 = time.perf_counter()
             t_pipeline = t_list = 0.0
             try:
+                # the result list is allocated while the first chunks are already in flight (10M slots: ~25 ms of page
+                # faults that used to sit in front of the pipeline)
+                out = [None] * n
                 while True:
                     lib.uml_async_poll(self._h, C.byref(rows_done), C.byref(finished))
                     if finished.value and not t_pipeline:
