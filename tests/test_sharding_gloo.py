@@ -77,6 +77,15 @@ class _StubEngine:
         self.calls.append((exact, src.size))
         return None, None
 
+    def predict_mlp(self, model, batch, exact=True, out_device_ptr=None, want_stats=True):
+        self.predict(model, batch, exact=exact, out_device_ptr=out_device_ptr, want_stats=want_stats)
+        self.calls[-1] = ("mlp",) + self.calls[-1]
+        return None, None
+
+
+class MlpModel:  # predict_sharded dispatches on the class name of the model handle (engine.MlpModel)
+    pass
+
 
 def _sharded_worker(rank, world, port, n_rows, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -95,6 +104,11 @@ def _sharded_worker(rank, world, port, n_rows, out_dir):
         got = predict_sharded(eng, model=None, batch=None, row_offset=lo, counts=counts, exact=True, labels_all=labels_all)
         np.testing.assert_array_equal(got.numpy(), full)
         assert eng.calls == [(True, hi - lo)]
+        # the 2-layer MLP goes through the same sharded path (cfg 5): predict_mlp on this rank's rows, same exchange
+        labels_all.fill_(-1)
+        got = predict_sharded(eng, model=MlpModel(), batch=None, row_offset=lo, counts=counts, exact=False, labels_all=labels_all)
+        np.testing.assert_array_equal(got.numpy(), full)
+        assert eng.calls[-1] == ("mlp", False, hi - lo)
         open(os.path.join(out_dir, f"sharded_ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
