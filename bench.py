@@ -41,7 +41,7 @@ UNIT = "rows/s"
 CONFIGS = {
     "cfg2": {
         "metric": "rows/sec batch predict (64->10 logistic)", "kind": "linear", "F": 64, "C": 10, "rows": 10_000_000,
-        "data": "digits", "kernel": "linear_argmax_tma_kernel<10, EXACT>", "cpu_rows": 2_000_000,
+        "data": "digits", "kernel": "linear_argmax_tma_kernel<10, EXACT, QUEUE> (fp64 re-score by a tenth warp of the same launch)", "cpu_rows": 2_000_000,
         "what": "BASELINE.json configs[1]: digits predictor (golden LogisticRegression 64->10)",
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch on 10M rows (profiles/r02_linear_argmax_tma_queue.ncu_raw.csv)
         "traffic_10m": 2_568_923_504, "traffic_src": "profiles/r02_linear_argmax_tma_queue.ncu_raw.csv (ncu --set full, per launch: dram read 2.560358 GB + write 8.565504 MB)",
