@@ -423,3 +423,52 @@ def test_mlp_layer_extraction():
         _mlp_layers(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2)))
     with pytest.raises(TypeError):
         _mlp_layers(nn.Linear(4, 2))
+
+
+def test_predictor_contract_checks_and_bookkeeping_without_a_gpu():
+    """Host-side guards of the drop-in predictor that never reach the device: classifier-only, dense weights, sklearn's
+    empty-batch error, the weights cache key (identity + fingerprints, no hashing per request) and the counters the
+    predictor publishes after a call."""
+    import warnings
+
+    from sklearn.linear_model import LinearRegression, Ridge
+
+    from unionml_b200 import predictors as P
+
+    X = np.random.default_rng(0).standard_normal((40, 5))
+    y = (X[:, 0] > 0).astype(int)
+    clf = LogisticRegression().fit(X, y)
+    P._check_linear_classifier(clf)
+    for reg in (LinearRegression().fit(X, X[:, 1]), Ridge().fit(X, X[:, 1])):
+        with pytest.raises(TypeError, match="classifiers"):
+            P._check_linear_classifier(reg)
+    sparse = LogisticRegression().fit(X, y).sparsify()
+    with pytest.raises(TypeError, match="dense"):
+        P._check_linear_classifier(sparse)
+
+    with pytest.raises(ValueError, match=r"0 sample\(s\)"):
+        P._check_min_samples(np.empty((0, 5)))
+    with pytest.raises(ValueError, match=r"0 sample\(s\)"):
+        P._check_min_samples(pd.DataFrame(np.empty((0, 5))))
+    P._check_min_samples(X)
+
+    k1 = P._weights_key(clf, None, None)
+    assert k1 == P._weights_key(clf, None, None)           # same arrays: same key, nothing hashed
+    clf.coef_ = clf.coef_.copy()                            # what `fit` does: rebinding is seen
+    assert P._weights_key(clf, None, None) != k1
+    k2 = P._weights_key(clf, None, None)
+    clf.coef_[0, 0] += 1.0                                  # in-place edit of a fingerprinted element is seen too
+    assert P._weights_key(clf, None, None) != k2
+    assert P._weights_key(clf, np.zeros(5), np.ones(5)) != P._weights_key(clf, np.zeros(5), 2 * np.ones(5))
+
+    P._ambiguous.update(last=0, total=0, warned=False)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        P._note_ambiguous({"n_ambiguous": 3, "h2d_bytes": 10, "path": 1})
+        P._note_ambiguous({"n_ambiguous": 2, "h2d_bytes": 20, "path": 1})
+    assert [w.category for w in caught] == [RuntimeWarning]            # once per process
+    assert P.last_ambiguous_rows() == 2 and P._ambiguous["total"] == 5
+    assert P.last_call_stats() == {"n_ambiguous": 2, "h2d_bytes": 20, "path": 1}
+    P._note_ambiguous({"n_ambiguous": 0})
+    assert P.last_ambiguous_rows() == 0
+    P._ambiguous.update(last=0, total=0, warned=False)
